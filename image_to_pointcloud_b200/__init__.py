@@ -1,0 +1,20 @@
+"""image_to_pointcloud_b200 -- B200 (sm_100a) implementation of one stage of
+Samsonboadi/Image_to_pointCloud: predicted depth map -> coloured 3-D point cloud
+(reference backend/app.py:174-250), behind the reference's own function signature.
+
+    from image_to_pointcloud_b200 import depth_to_point_cloud      # drop-in for app.py:174
+
+The package holds only what that path needs: ``csrc/`` (CUDA kernels + the C ABI declared in
+``include/d2pc.h``), the ctypes binding, and the host-side mirror of the reference interface.
+"""
+from .api import depth_to_point_cloud, depth_to_point_cloud_batch
+from .engine import DENSITY_STEP, EmitResult, FrameEngine, reference_intrinsics, shard_frames
+from .hostpipe import HostFramePipeline
+from ._lib import D2pcConfig, D2pcError, D2pcFrameParams, load_library
+
+__all__ = [
+    "depth_to_point_cloud", "depth_to_point_cloud_batch", "FrameEngine", "HostFramePipeline",
+    "EmitResult", "DENSITY_STEP", "reference_intrinsics", "shard_frames",
+    "D2pcConfig", "D2pcFrameParams", "D2pcError", "load_library",
+]
+__version__ = "0.1.0"

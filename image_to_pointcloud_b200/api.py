@@ -1,0 +1,144 @@
+"""Drop-in for the reference's ``depth_to_point_cloud`` (reference backend/app.py:174-250).
+
+    points, colors = depth_to_point_cloud(image, depth, density=..., invert=..., depth_scale=...,
+                                          smooth=..., fov=...)
+
+is what ``process_image_pipeline`` calls (backend/app.py:468-476).  Same positional signature,
+same return value (two C-contiguous float32 [N,3] NumPy arrays on the host, row
+``i = (v/step) * ceil(W/step) + (u/step)``), same error convention (exceptions; ``KeyError`` for an
+unknown density).  Extensions are keyword-only and default to "off": ``z_range`` (depth-range mask
+with ordered compaction), ``drop_nonfinite``, ``voxel_size`` (voxel-grid down-sampling).
+
+All arithmetic runs in the sm_100a kernels of libd2pc.so.  There is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .engine import DENSITY_STEP, EmitResult, FrameEngine
+
+logger = logging.getLogger(__name__)
+
+_ENGINES: Dict[tuple, "FrameEngine"] = {}
+_STAGING: Dict[tuple, dict] = {}
+
+
+def _engine_for(img_h, img_w, img_c, dep_h, dep_w, device) -> FrameEngine:
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    key = (str(dev), img_h, img_w, img_c, dep_h, dep_w)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        if len(_ENGINES) > 8:  # geometry changes per upload in the web app; keep the cache small
+            _ENGINES.clear()
+            _STAGING.clear()
+        eng = FrameEngine(img_h, img_w, dep_h, dep_w, batch=1, img_c=img_c, device=dev)
+        _ENGINES[key] = eng
+        with torch.cuda.device(dev):
+            _STAGING[key] = dict(
+                depth_pin=torch.empty((1, dep_h, dep_w), dtype=torch.float32).pin_memory(),
+                depth_dev=torch.empty((1, dep_h, dep_w), dtype=torch.float32, device=dev),
+                bgr_pin=(torch.empty((1, img_h, img_w, img_c), dtype=torch.uint8).pin_memory()
+                         if img_c >= 3 else None),
+                bgr_dev=(torch.empty((1, img_h, img_w, img_c), dtype=torch.uint8, device=dev)
+                         if img_c >= 3 else None),
+                count_pin=torch.zeros(1, dtype=torch.int32).pin_memory(),
+            )
+    return eng
+
+
+def _image_channels(image: np.ndarray) -> int:
+    # reference: colours come from image[v, u][:3] when ndim == 3 and shape[2] >= 3, else grey 128
+    if image.ndim == 3 and image.shape[2] >= 3:
+        if image.shape[2] not in (3, 4):
+            raise ValueError("images with more than 4 channels are not supported")
+        return int(image.shape[2])
+    return 1
+
+
+def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
+                         density: str = "medium",
+                         invert: bool = True,
+                         depth_scale: float = 10.0,
+                         smooth: bool = False,
+                         smooth_ksize: int = 5,
+                         fov: Optional[float] = None,
+                         *,
+                         z_range: Optional[Tuple[float, float]] = None,
+                         drop_nonfinite: bool = False,
+                         voxel_size: Optional[float] = None,
+                         return_voxel_index: bool = False,
+                         device=None) -> tuple:
+    """Convert a depth map to a coloured 3-D point cloud on a B200 (see module docstring)."""
+    try:
+        if not isinstance(image, np.ndarray) or not isinstance(depth, np.ndarray):
+            raise TypeError("image and depth must be numpy arrays")
+        img_h, img_w = image.shape[:2]
+        dep_h, dep_w = depth.shape[:2]
+        step = DENSITY_STEP[density]  # noqa: F841  (KeyError like the reference, before any work)
+        if smooth:
+            raise NotImplementedError("smooth=True (reference app.py:208-214) is not implemented yet")
+        if image.dtype != np.uint8:
+            raise TypeError("image must be uint8 (cv2.imdecode output)")
+        img_c = _image_channels(image)
+        eng = _engine_for(int(img_h), int(img_w), img_c, int(dep_h), int(dep_w), device)
+        st = _STAGING[(str(eng.device), int(img_h), int(img_w), img_c, int(dep_h), int(dep_w))]
+        want_voxel = voxel_size is not None
+        cfg = eng.make_config(density=density, invert=invert, depth_scale=float(depth_scale), fov=fov,
+                              z_range=z_range, drop_nonfinite=drop_nonfinite, want_bounds=want_voxel)
+        stream = torch.cuda.current_stream(eng.device)
+        with torch.cuda.device(eng.device):
+            # host -> pinned staging -> device (d = depth.astype(np.float32), app.py:191)
+            st["depth_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(depth, dtype=np.float32).reshape(dep_h, dep_w)))
+            st["depth_dev"].copy_(st["depth_pin"], non_blocking=True)
+            if img_c >= 3:
+                st["bgr_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(image)))
+                st["bgr_dev"].copy_(st["bgr_pin"], non_blocking=True)
+            res = eng.process(cfg, st["depth_dev"], st["bgr_dev"], stream=stream)
+            if want_voxel:
+                vxyz, vrgb, vidx, vcount = eng.voxel_downsample(cfg, res, float(voxel_size),
+                                                                want_index=return_voxel_index, stream=stream)
+                n = int(vcount.cpu()[0])
+                out = (_to_host(vxyz[0, :n]), _to_host(vrgb[0, :n]))
+                if return_voxel_index:
+                    out = out + (vidx[0, :n].cpu().numpy(),)
+                return out
+            n = int(res.count.cpu()[0])
+            return _to_host(res.xyz[0, :n]), _to_host(res.rgb[0, :n])
+    except Exception as e:  # same convention as the reference (app.py:248-250): log and re-raise
+        logger.error(f"Error in point cloud generation: {str(e)}")
+        raise
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device rows -> a fresh C-contiguous float32 NumPy array (pinned host memory from torch's
+    caching host allocator, so the copy runs at PCIe speed; the array owns its buffer)."""
+    host = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    host.copy_(t, non_blocking=False)
+    return host.numpy()
+
+
+def depth_to_point_cloud_batch(images: Sequence[np.ndarray], depths: Sequence[np.ndarray],
+                               density: str = "medium", invert: bool = True, depth_scale: float = 10.0,
+                               fov: Optional[float] = None, *, z_range=None, drop_nonfinite: bool = False,
+                               chunk: int = 8, device=None):
+    """Many frames of one geometry through the same path: list of (points, colors) per frame.
+
+    Host buffers in, host buffers out.  Frames are processed ``chunk`` at a time with three
+    streams (H2D / kernels / D2H) and double-buffered pinned staging, so copies overlap compute.
+    """
+    from .hostpipe import HostFramePipeline
+    if len(images) != len(depths):
+        raise ValueError("images and depths differ in length")
+    if len(images) == 0:
+        return []
+    img_h, img_w = images[0].shape[:2]
+    dep_h, dep_w = depths[0].shape[:2]
+    img_c = _image_channels(images[0])
+    pipe = HostFramePipeline(img_h, img_w, dep_h, dep_w, img_c=img_c, chunk=min(chunk, len(images)),
+                             density=density, invert=invert, depth_scale=depth_scale, fov=fov,
+                             z_range=z_range, drop_nonfinite=drop_nonfinite, device=device)
+    return pipe.run(images, depths)

@@ -1,0 +1,230 @@
+// d2pc_device.cuh -- shared by the sm_100a translation units: per-frame state block, workspace
+// layout, launch geometry and small warp/block primitives.
+#ifndef D2PC_DEVICE_CUH_
+#define D2PC_DEVICE_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "d2pc_math.h"
+
+namespace d2pc {
+
+// ------------------------------------------------------------------------------------------
+// tunables
+// ------------------------------------------------------------------------------------------
+constexpr int kSampleSize = 8192;      // level-1 sample per frame (stratified), power of two
+constexpr int kSample2Size = 4096;     // level-2 sample over a bracket's candidates
+constexpr int kSortCap = 16384;        // keys one CTA sorts in shared memory (64 KB)
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 16;
+constexpr int kScanTile = kScanThreads * kScanPerThread;  // 4096 pixels per CTA
+constexpr int kSelThreads = 1024;
+constexpr int kEmitThreads = 256;
+constexpr int kEmitPerThread = 4;
+constexpr int kEmitTile = kEmitThreads * kEmitPerThread;  // 1024 output points per CTA
+constexpr int kFbTargets = 4;          // simultaneous ranks in the fallback radix select
+constexpr uint32_t kCandDivisor = 16;  // candidate capacity per bracket = max(n/16, ...)
+
+// ------------------------------------------------------------------------------------------
+// geometry derived from D2pcConfig (host computes once, passed by value to kernels)
+// ------------------------------------------------------------------------------------------
+struct Geom {
+  int32_t H, W, C, h, w, step;
+  int32_t nu, nv;        // output grid: ceil(W/step) x ceil(H/step)
+  uint32_t P;            // H*W   pixels of the (virtually resized) map = n of the percentiles
+  uint32_t N;            // nu*nv output rows per frame (capacity of the output slot)
+  uint32_t D;            // h*w   elements of one depth frame
+  int32_t native;        // (h, w) == (H, W)
+  double scale_x, scale_y;  // (double)w / W, (double)h / H   (bilinear coordinate scale)
+};
+
+inline Geom make_geom(const D2pcConfig &c) {
+  Geom g;
+  g.H = c.img_h; g.W = c.img_w; g.C = c.img_c; g.h = c.dep_h; g.w = c.dep_w; g.step = c.step;
+  g.nu = (c.img_w + c.step - 1) / c.step;
+  g.nv = (c.img_h + c.step - 1) / c.step;
+  g.P = (uint32_t)c.img_h * (uint32_t)c.img_w;
+  g.N = (uint32_t)g.nu * (uint32_t)g.nv;
+  g.D = (uint32_t)c.dep_h * (uint32_t)c.dep_w;
+  g.native = (c.dep_h == c.img_h && c.dep_w == c.img_w) ? 1 : 0;
+  g.scale_x = (double)c.dep_w / (double)c.img_w;
+  g.scale_y = (double)c.dep_h / (double)c.img_h;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-frame state (lives in the caller's workspace)
+// ------------------------------------------------------------------------------------------
+struct __align__(256) FrameState {
+  // level-1 brackets (inclusive key bounds) for the 2% / 98% order statistics
+  uint32_t brL[2], brU[2];
+  uint32_t sample_ok;     // 0: sample saw a non-finite value
+  // streaming pass results (atomically accumulated by scan CTAs)
+  uint32_t below[2];      // finite keys <  brL
+  uint32_t eqL[2];        // finite keys == brL
+  uint32_t inside[2];     // finite keys strictly inside (brL, brU); appended to the candidate list
+  uint32_t eqU[2];        // finite keys == brU (brU != brL)
+  uint32_t n_nonfinite, n_nan;
+  uint32_t min_key, max_key;  // over finite values
+  // exact selection
+  uint32_t sel_key[4];    // keys at ranks lo2, hi2, lo98, hi98
+  uint32_t sel_fail;
+  uint32_t sel_done;      // bracket CTAs finished (0..2)
+  int32_t status;         // D2PC_FRAME_*
+  // fallback radix select
+  uint32_t fb_prefix[kFbTargets];
+  uint32_t fb_rank[kFbTargets];
+  uint32_t fb_active;     // number of live targets in the current stage
+  uint32_t fb_any_nan;    // repaired map still holds NaN (median itself NaN)
+  // emit
+  uint32_t emit_count;
+  uint32_t bounds_min[3], bounds_max[3];  // ordered keys of kept x, y, z
+  // parameters consumed by emit
+  NormParams norm;
+};
+
+struct WsLayout {
+  size_t state_off, cand_off, tile_off, fbhist_off, total;
+  uint32_t cand_cap;      // keys per (frame, bracket)
+  uint32_t emit_tiles;    // emit CTAs per frame
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline WsLayout make_layout(const D2pcConfig &c) {
+  Geom g = make_geom(c);
+  WsLayout L;
+  uint32_t cap = g.P / kCandDivisor + 1;
+  uint32_t small = g.P < (uint32_t)kSortCap ? g.P : (uint32_t)kSortCap;
+  if (cap < small) cap = small;
+  cap = (cap + 3u) & ~3u;
+  L.cand_cap = cap;
+  L.emit_tiles = (g.N + kEmitTile - 1) / kEmitTile;
+  size_t off = 0;
+  L.state_off = off;  off = align_up(off + sizeof(FrameState) * (size_t)c.batch, 256);
+  L.cand_off = off;   off = align_up(off + (size_t)c.batch * 2 * cap * sizeof(uint32_t), 256);
+  L.tile_off = off;   off = align_up(off + (size_t)c.batch * L.emit_tiles * sizeof(unsigned long long), 256);
+  L.fbhist_off = off; off = align_up(off + (size_t)c.batch * kFbTargets * 256 * sizeof(uint32_t), 256);
+  L.total = off;
+  return L;
+}
+
+// everything a kernel needs to find its frame's data
+struct KParams {
+  Geom g;
+  int32_t batch;
+  const float *depth;       // [batch, h, w]
+  FrameState *state;        // [batch]
+  uint32_t *cand;           // [batch][2][cand_cap]
+  unsigned long long *tile_state;  // [batch][emit_tiles]
+  uint32_t *fb_hist;        // [batch][kFbTargets][256]
+  uint32_t cand_cap, emit_tiles;
+  int32_t force_fallback;
+};
+
+inline KParams make_kparams(const D2pcConfig &c, const float *d_depth, void *ws) {
+  KParams k;
+  WsLayout L = make_layout(c);
+  char *base = (char *)ws;
+  k.g = make_geom(c);
+  k.batch = c.batch;
+  k.depth = d_depth;
+  k.state = (FrameState *)(base + L.state_off);
+  k.cand = (uint32_t *)(base + L.cand_off);
+  k.tile_state = (unsigned long long *)(base + L.tile_off);
+  k.fb_hist = (uint32_t *)(base + L.fbhist_off);
+  k.cand_cap = L.cand_cap;
+  k.emit_tiles = L.emit_tiles;
+  k.force_fallback = c.force_fallback;
+  return k;
+}
+
+int validate_config(const D2pcConfig *cfg);   // d2pc_api.cu
+int record_cuda_error(cudaError_t e);          // d2pc_api.cu: returns D2PC_ERR_CUDA, stores text
+
+#define D2PC_CHECK_LAUNCH()                                  \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return record_cuda_error(e__);   \
+  } while (0)
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------
+// device primitives
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float *p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_f1(float *p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Bitonic sort of n (power of two) uint32 keys in shared memory by the whole CTA, ascending.
+__device__ __forceinline__ void block_bitonic_sort(uint32_t *s, uint32_t n) {
+  const uint32_t half = n >> 1;
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+        uint32_t a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        uint32_t b = a | j;
+        uint32_t x = s[a], y = s[b];
+        bool up = (a & k) == 0;
+        if ((x > y) == up) { s[a] = y; s[b] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+// Raw value of pixel p (row-major index into the H x W grid) of one frame's (virtually resized)
+// depth map.  NATIVE: the depth map already has the image size.
+template <bool NATIVE>
+__device__ __forceinline__ float depth_at(const float *frame, const Geom &g, uint32_t p) {
+  if (NATIVE) {
+    return __ldg(frame + p);
+  } else {
+    uint32_t v = p / (uint32_t)g.W;
+    uint32_t u = p - v * (uint32_t)g.W;
+    AxisTap tx = axis_tap((int32_t)u, g.scale_x, g.w);
+    AxisTap ty = axis_tap((int32_t)v, g.scale_y, g.h);
+    return bilinear_sample(frame, g.w, tx, ty);
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace d2pc
+#endif  // D2PC_DEVICE_CUH_

@@ -1,0 +1,337 @@
+// d2pc_emit.cu -- reference steps a4..a11 (backend/app.py:200-246) plus the ax-1 extension,
+// fused into one pass per output point:
+//   (resize) -> non-finite repair -> clip/normalise -> invert -> scale -> back-projection ->
+//   BGR->RGB gather -> (depth-range mask -> ordered compaction) -> AoS float32 packing.
+//
+// Memory plan (HBM-bound by design: 4 B depth + 3 B BGR in, 24 B out per point):
+//   * emit_fast_kernel: stride 1, native-size depth, BGR, no mask.  Each thread owns 4
+//     consecutive pixels: one 16 B depth load, three 4 B colour loads, FP64 chain in registers,
+//     12-byte AoS records staged through shared memory so that every global store is a full,
+//     16 B-aligned, coalesced st.global.cs.v4 (streaming: the output is never re-read).
+//   * emit_generic_kernel: any stride / resized depth / BGRA / grey / mask.  Same staging; the
+//     compacted rows of a tile go to `prefix` rows found by a decoupled look-back over the
+//     frame's tiles, so the output keeps raster order (the reference's preview stride
+//     points[::stride], app.py:498-500, depends on it).
+#include "d2pc_device.cuh"
+
+namespace d2pc {
+
+struct EmitArgs {
+  const uint8_t *bgr;
+  float *xyz, *rgb;
+  uint32_t *count;
+  PixelConsts pc;
+  int32_t use_z, drop_nf, want_bounds;
+  float z_min, z_max;
+};
+
+__device__ __forceinline__ void stage_f4(float *s, float a, float b, float c, float d) {
+  *reinterpret_cast<float4 *>(s) = make_float4(a, b, c, d);
+}
+
+// per-CTA reduction of kept-point bounds -> 6 global atomics on ordered keys
+__device__ __forceinline__ void reduce_bounds(FrameState *fs, uint32_t mn[3], uint32_t mx[3],
+                                              uint32_t (*s_b)[kEmitThreads / 32]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint32_t a = warp_min(mn[c]), b = warp_max(mx[c]);
+    if (lane == 0) { s_b[c][warp] = a; s_b[3 + c][warp] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int c = threadIdx.x;
+    uint32_t r = s_b[c][0];
+    for (int w = 1; w < kEmitThreads / 32; ++w) r = c < 3 ? min(r, s_b[c][w]) : max(r, s_b[c][w]);
+    if (c < 3) { if (r != 0xFFFFFFFFu) atomicMin(&fs->bounds_min[c], r); }
+    else       { if (r != 0u) atomicMax(&fs->bounds_max[c - 3], r); }
+  }
+}
+
+// Copy n_f floats from shared staging (whose word 0 corresponds to global float index
+// g0 - s_off, i.e. staging is offset so that src and dst share 16 B alignment) to global.
+__device__ __forceinline__ void copy_out(const float *s, uint32_t s_off, uint32_t n_f, float *gbase,
+                                         size_t g0) {
+  float *galigned = gbase + (g0 - s_off);
+  const uint32_t span = s_off + n_f;
+  const uint32_t chunks = (span + 3u) >> 2;
+  for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x) {
+    const uint32_t w = c << 2;
+    if (w >= s_off && w + 4u <= span) {
+      stg_stream_f4(galigned + w, *reinterpret_cast<const float4 *>(s + w));
+    } else {
+      for (uint32_t k = 0; k < 4u; ++k)
+        if (w + k >= s_off && w + k < span) stg_stream_f1(galigned + w + k, s[w + k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path: step 1, native depth, 3-channel image, P % 4 == 0, no mask
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEmitThreads) emit_fast_kernel(KParams kp, EmitArgs ea) {
+  __shared__ __align__(16) float s_xyz[kEmitTile * 3];
+  __shared__ __align__(16) float s_rgb[kEmitTile * 3];
+  __shared__ uint32_t s_b[6][kEmitThreads / 32];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_READY) return;
+  const NormParams np_ = fs->norm;
+  const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
+  const uint32_t tile_base = blockIdx.x * (uint32_t)kEmitTile;
+  const uint32_t p0 = tile_base + 4u * (uint32_t)tid;
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  if (p0 < P) {
+    const float4 d4 = ldg_stream_f4(kp.depth + (size_t)b * P + p0);
+    const uint8_t *cp = ea.bgr + ((size_t)b * P + p0) * 3;
+    const uint32_t c0 = ldg_stream_u32(cp), c1 = ldg_stream_u32(cp + 4), c2 = ldg_stream_u32(cp + 8);
+    uint32_t v = p0 / W, u = p0 - v * W;
+    const float raw[4] = {d4.x, d4.y, d4.z, d4.w};
+    float o[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (u >= W) { u -= W; v += 1; }
+      const double n = normalised_depth(raw[k], np_, ea.pc.invert);
+      back_project(n, (int32_t)u, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+      u += 1;
+    }
+    if (ea.want_bounds) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t key = float_to_key(o[3 * k + c]);
+          mn[c] = min(mn[c], key); mx[c] = max(mx[c], key);
+        }
+    }
+    float *sx = s_xyz + 12 * tid;
+    stage_f4(sx, o[0], o[1], o[2], o[3]);
+    stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
+    stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
+    // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
+    float *sr = s_rgb + 12 * tid;
+    stage_f4(sr, (float)((c0 >> 16) & 255u), (float)((c0 >> 8) & 255u), (float)(c0 & 255u),
+             (float)((c1 >> 8) & 255u));
+    stage_f4(sr + 4, (float)(c1 & 255u), (float)(c0 >> 24), (float)(c2 & 255u), (float)(c1 >> 24));
+    stage_f4(sr + 8, (float)((c1 >> 16) & 255u), (float)(c2 >> 24), (float)((c2 >> 16) & 255u),
+             (float)((c2 >> 8) & 255u));
+  }
+  __syncthreads();
+  const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
+  const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
+  const uint32_t nvec = rows * 3u / 4u;  // rows % 4 == 0 here
+  for (uint32_t i = tid; i < nvec; i += kEmitThreads) {
+    stg_stream_f4(ea.xyz + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_xyz + 4 * i));
+    stg_stream_f4(ea.rgb + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_rgb + 4 * i));
+  }
+  if (blockIdx.x == 0 && tid == 0) ea.count[b] = kp.g.N;
+  if (ea.want_bounds) reduce_bounds(fs, mn, mx, s_b);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path
+// ------------------------------------------------------------------------------------------
+// tile_state word: (flag << 32) | value ; flag 0 = not ready, 1 = tile aggregate, 2 = inclusive
+__device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long long *ts, int tile) {
+  const int lane = threadIdx.x & 31;
+  uint32_t exclusive = 0;
+  int base_idx = tile - 1;
+  while (true) {
+    const int idx = base_idx - lane;
+    unsigned long long st = (idx >= 0) ? ts[idx] : ((2ull << 32) | 0ull);
+    const uint32_t flag = (uint32_t)(st >> 32);
+    const unsigned inval = __ballot_sync(0xffffffffu, flag == 0u);
+    const unsigned incl = __ballot_sync(0xffffffffu, flag == 2u);
+    const int first_incl = incl ? (__ffs(incl) - 1) : 32;
+    const unsigned need = first_incl >= 31 ? 0xffffffffu : ((2u << first_incl) - 1u);
+    if (inval & need) continue;  // a needed predecessor has not published yet: re-read
+    uint32_t val = (lane <= first_incl) ? (uint32_t)st : 0u;
+    exclusive += warp_sum(val);
+    if (first_incl < 32) break;
+    base_idx -= 32;
+  }
+  return exclusive;
+}
+
+template <bool NATIVE, bool MASK>
+__global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, EmitArgs ea) {
+  __shared__ __align__(16) float s_xyz[kEmitTile * 3 + 4];
+  __shared__ __align__(16) float s_rgb[kEmitTile * 3 + 4];
+  __shared__ uint32_t s_warp[kEmitThreads / 32];
+  __shared__ uint32_t s_prefix, s_total;
+  __shared__ uint32_t s_b[6][kEmitThreads / 32];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_READY) return;
+  const NormParams np_ = fs->norm;
+  const Geom &g = kp.g;
+  const float *frame = kp.depth + (size_t)b * g.D;
+  const uint32_t tile_base = (uint32_t)tile * (uint32_t)kEmitTile;
+  const uint32_t i0 = tile_base + (uint32_t)kEmitPerThread * (uint32_t)tid;
+  float o[12], col[12];
+  bool keep[4];
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  uint32_t my_cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = i0 + k;
+    keep[k] = false;
+    if (i >= g.N) continue;
+    const uint32_t jv = i / (uint32_t)g.nu, ju = i - jv * (uint32_t)g.nu;
+    const uint32_t u = ju * (uint32_t)g.step, v = jv * (uint32_t)g.step;
+    const uint32_t p = v * (uint32_t)g.W + u;
+    const float raw = depth_at<NATIVE>(frame, g, p);
+    const double n = normalised_depth(raw, np_, ea.pc.invert);
+    back_project(n, (int32_t)u, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+    if (g.C >= 3) {
+      const uint8_t *cp = ea.bgr + ((size_t)b * g.P + p) * (size_t)g.C;
+      col[3 * k + 0] = (float)cp[2];
+      col[3 * k + 1] = (float)cp[1];
+      col[3 * k + 2] = (float)cp[0];
+    } else {
+      col[3 * k + 0] = col[3 * k + 1] = col[3 * k + 2] = 128.0f;
+    }
+    bool kk = true;
+    if (MASK) {
+      const float z = o[3 * k + 2];
+      if (ea.use_z) kk = (z >= ea.z_min) && (z <= ea.z_max);
+      if (ea.drop_nf && !is_finite_f32(raw)) kk = false;
+    }
+    keep[k] = kk;
+    if (kk) {
+      my_cnt++;
+      if (ea.want_bounds) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t key = float_to_key(o[3 * k + c]);
+          mn[c] = min(mn[c], key); mx[c] = max(mx[c], key);
+        }
+      }
+    }
+  }
+
+  // local offsets: exclusive scan of my_cnt over the CTA
+  uint32_t incl = my_cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t warp_off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kEmitThreads / 32; ++w) {
+    uint32_t c = s_warp[w];
+    if (w < warp) warp_off += c;
+    total += c;
+  }
+  uint32_t local = warp_off + incl - my_cnt;
+
+  // destination row of this tile
+  uint32_t dest_row;
+  if (MASK) {
+    volatile unsigned long long *ts = kp.tile_state + (size_t)b * kp.emit_tiles;
+    if (warp == 0) {
+      if (lane == 0 && tile > 0) ts[tile] = (1ull << 32) | (unsigned long long)total;
+      uint32_t ex = (tile == 0) ? 0u : lookback_exclusive(ts, tile);
+      if (lane == 0) {
+        ts[tile] = (2ull << 32) | (unsigned long long)(ex + total);
+        s_prefix = ex;
+        if (tile == (int)kp.emit_tiles - 1) ea.count[b] = ex + total;
+      }
+    }
+    __syncthreads();
+    dest_row = s_prefix;
+  } else {
+    dest_row = tile_base;
+    if (tile == 0 && tid == 0) ea.count[b] = g.N;
+  }
+
+  const size_t g0 = ((size_t)b * g.N + dest_row) * 3;
+  const uint32_t s_off = (uint32_t)(g0 & 3);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!keep[k]) continue;
+    const uint32_t w = s_off + 3u * local;
+    s_xyz[w] = o[3 * k]; s_xyz[w + 1] = o[3 * k + 1]; s_xyz[w + 2] = o[3 * k + 2];
+    s_rgb[w] = col[3 * k]; s_rgb[w + 1] = col[3 * k + 1]; s_rgb[w + 2] = col[3 * k + 2];
+    local++;
+  }
+  __syncthreads();
+  copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0);
+  copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0);
+  if (ea.want_bounds) reduce_bounds(fs, mn, mx, s_b);
+}
+
+__global__ void emit_init_kernel(KParams kp, int clear_tiles) {
+  const int b = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  if (threadIdx.x == 0) {
+    fs->emit_count = 0;
+    for (int c = 0; c < 3; ++c) { fs->bounds_min[c] = 0xFFFFFFFFu; fs->bounds_max[c] = 0u; }
+  }
+  if (clear_tiles) {
+    unsigned long long *ts = kp.tile_state + (size_t)b * kp.emit_tiles;
+    for (uint32_t i = threadIdx.x; i < kp.emit_tiles; i += blockDim.x) ts[i] = 0ull;
+  }
+}
+
+// bounds keys -> floats; an empty frame (no kept point) reports NaN bounds
+__global__ void bounds_export_kernel(KParams kp, float *d_bounds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kp.batch * 6) return;
+  const int b = i / 6, c = i % 6;
+  const FrameState &fs = kp.state[b];
+  const bool empty = fs.bounds_min[0] == 0xFFFFFFFFu && fs.bounds_max[0] == 0u;
+  uint32_t key = c < 3 ? fs.bounds_min[c] : fs.bounds_max[c - 3];
+  d_bounds[i] = empty ? nan_f32() : key_to_float(key);
+}
+
+}  // namespace d2pc
+
+using namespace d2pc;
+
+extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
+                                 void *d_workspace, size_t workspace_bytes, float *d_xyz,
+                                 float *d_rgb, uint32_t *d_count, float *d_bounds, void *stream) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!d_workspace || !d_depth || !d_xyz || !d_rgb || !d_count) return D2PC_ERR_INVALID_ARGUMENT;
+  if (cfg->img_c >= 3 && !d_bgr) return D2PC_ERR_INVALID_ARGUMENT;
+  if (cfg->want_bounds && !d_bounds) return D2PC_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < make_layout(*cfg).total) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)d_xyz | (uintptr_t)d_rgb) & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  EmitArgs ea;
+  ea.bgr = d_bgr; ea.xyz = d_xyz; ea.rgb = d_rgb; ea.count = d_count;
+  ea.pc.scale = cfg->depth_scale; ea.pc.cx = cfg->cx; ea.pc.cy = cfg->cy; ea.pc.f = cfg->f;
+  ea.pc.inv_f = 1.0 / cfg->f; ea.pc.invert = cfg->invert;
+  ea.use_z = cfg->use_z_range; ea.drop_nf = cfg->drop_nonfinite; ea.want_bounds = cfg->want_bounds;
+  ea.z_min = cfg->z_min; ea.z_max = cfg->z_max;
+  const bool mask = cfg->use_z_range || cfg->drop_nonfinite;
+  if (mask || cfg->want_bounds) {
+    emit_init_kernel<<<cfg->batch, 256, 0, st>>>(kp, mask ? 1 : 0);
+    D2PC_CHECK_LAUNCH();
+  }
+  dim3 grid(kp.emit_tiles, cfg->batch);
+  const bool fast = !mask && kp.g.native && cfg->step == 1 && cfg->img_c == 3 && (kp.g.P & 3u) == 0u &&
+                    (((uintptr_t)d_depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u);
+  if (fast) {
+    emit_fast_kernel<<<grid, kEmitThreads, 0, st>>>(kp, ea);
+  } else if (kp.g.native) {
+    if (mask) emit_generic_kernel<true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);
+    else emit_generic_kernel<true, false><<<grid, kEmitThreads, 0, st>>>(kp, ea);
+  } else {
+    if (mask) emit_generic_kernel<false, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);
+    else emit_generic_kernel<false, false><<<grid, kEmitThreads, 0, st>>>(kp, ea);
+  }
+  D2PC_CHECK_LAUNCH();
+  if (cfg->want_bounds) {
+    bounds_export_kernel<<<(cfg->batch * 6 + 127) / 128, 128, 0, st>>>(kp, d_bounds);
+    D2PC_CHECK_LAUNCH();
+  }
+  return D2PC_OK;
+}

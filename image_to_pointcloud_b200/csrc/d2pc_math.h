@@ -1,0 +1,269 @@
+// d2pc_math.h -- per-pixel and per-frame arithmetic of the depth -> point-cloud stage, written
+// once for host and device so the same code can be checked on a CPU (tests/test_host_math.py
+// builds it with g++ as libd2pc_hostmath.so) and then run inside the sm_100a kernels.
+//
+// Every function cites the reference step it restates (reference backend/app.py:174-250) or the
+// third-party arithmetic that step calls.  Bit-exactness rules:
+//   * no floating-point contraction anywhere: nvcc is invoked with --fmad=false and g++ with
+//     -ffp-contract=off; the only fused operations are the explicit fma()/fmaf() calls below;
+//   * the per-pixel chain runs in float64 exactly as NumPy >= 2 runs it (NEP 50 promotes the
+//     clip/normalise/invert chain to float64 because np.percentile returns float64 scalars);
+//   * divisions by per-frame constants use a reciprocal + two FMA correction steps that return
+//     the correctly rounded quotient (see div_by_const), never an approximation.
+#ifndef D2PC_MATH_H_
+#define D2PC_MATH_H_
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/d2pc.h"
+
+#if defined(__CUDACC__)
+#define D2PC_HD __host__ __device__ __forceinline__
+#else
+#define D2PC_HD static inline
+#endif
+
+namespace d2pc {
+
+// ---------------------------------------------------------------------------------------------
+// bit casts and the order-preserving float32 <-> uint32 key
+// ---------------------------------------------------------------------------------------------
+D2PC_HD uint32_t f32_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+D2PC_HD float bits_f32(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+// Monotone map: a < b (as floats, -0 < +0 by convention)  <=>  key(a) < key(b).
+// -inf -> 0x007FFFFF, +inf -> 0xFF800000; NaNs fall outside [key(-inf), key(+inf)].
+D2PC_HD uint32_t float_to_key(float f) {
+  uint32_t b = f32_bits(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+D2PC_HD float key_to_float(uint32_t k) {
+  return bits_f32((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+#define D2PC_KEY_NEG_INF 0x007FFFFFu
+#define D2PC_KEY_POS_INF 0xFF800000u
+
+D2PC_HD bool is_finite_f32(float f) { return (f32_bits(f) & 0x7F800000u) != 0x7F800000u; }
+D2PC_HD bool is_nan_f32(float f) { return (f32_bits(f) & 0x7FFFFFFFu) > 0x7F800000u; }
+D2PC_HD bool is_inf_f32(float f) { return (f32_bits(f) & 0x7FFFFFFFu) == 0x7F800000u; }
+D2PC_HD float nan_f32() { return bits_f32(0x7FC00000u); }
+
+// ---------------------------------------------------------------------------------------------
+// a1  bilinear resize taps -- cv2.resize(INTER_LINEAR) float32, IPP path (call site app.py:188)
+// ---------------------------------------------------------------------------------------------
+struct AxisTap {
+  int32_t i0, i1;  // source indices (i1 == i0 when clamped)
+  float t;         // weight of tap 1, float32 cast of the float64 fraction
+  int32_t clamped; // coordinate fell outside [0, n_src-1): output copies tap 0
+};
+
+// scale = (double)n_src / (double)n_dst (computed once by the caller, one IEEE division).
+D2PC_HD AxisTap axis_tap(int32_t d, double scale, int32_t n_src) {
+  AxisTap a;
+  double f = ((double)d + 0.5) * scale - 0.5;  // two roundings; contraction is disabled
+  double fl = floor(f);
+  double t = f - fl;
+  int32_t i0 = (int32_t)fl;
+  a.clamped = 0;
+  if (i0 < 0) {
+    i0 = 0;
+    t = 0.0;
+    a.clamped = 1;
+  }
+  if (i0 >= n_src - 1) {
+    i0 = n_src - 1;
+    t = 0.0;
+    a.clamped = 1;
+  }
+  a.i0 = i0;
+  a.i1 = a.clamped ? i0 : i0 + 1;
+  a.t = (float)t;
+  return a;
+}
+
+// Horizontal pass on one source row: r = fmaf(S[x1] - S[x0], tx, S[x0]); clamped -> copy.
+D2PC_HD float lerp_tap(float a, float b, float t, int32_t clamped) {
+  if (clamped) return a;
+  float diff = b - a;  // rounded float32 subtraction
+  return fmaf(diff, t, a);
+}
+
+// Full 2-D sample at destination (xtap, ytap) from a source image with row pitch src_w.
+D2PC_HD float bilinear_sample(const float *src, int32_t src_w, const AxisTap &tx,
+                              const AxisTap &ty) {
+  const float *row0 = src + (size_t)ty.i0 * src_w;
+  float r0 = lerp_tap(row0[tx.i0], row0[tx.i1], tx.t, tx.clamped);
+  float out;
+  if (ty.clamped) {
+    out = r0;
+    // corner blocks (both clamped): IPP runs arithmetic there; +-inf comes out as NaN
+    if (tx.clamped && is_inf_f32(out)) out = nan_f32();
+  } else {
+    const float *row1 = src + (size_t)ty.i1 * src_w;
+    float r1 = lerp_tap(row1[tx.i0], row1[tx.i1], tx.t, tx.clamped);
+    out = lerp_tap(r0, r1, ty.t, 0);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3  np.percentile(d, [2, 98]), method "linear" (numpy 2.3.5 _quantile/_lerp; app.py:197)
+// ---------------------------------------------------------------------------------------------
+struct RankPair {
+  uint32_t lo, hi;  // 0-based ranks of the two neighbours in sorted order
+  double gamma;     // interpolation weight
+};
+D2PC_HD RankPair percentile_ranks(uint32_t n, double q) {
+  RankPair r;
+  double vi = (double)(n - 1) * q;
+  if (vi >= (double)(n - 1)) {  // _get_indexes: both neighbours = last element, gamma = vi+1
+    r.lo = r.hi = n - 1;
+    r.gamma = vi + 1.0;
+  } else {
+    double fl = floor(vi);
+    r.lo = (uint32_t)fl;
+    r.hi = r.lo + 1;
+    r.gamma = vi - fl;
+  }
+  return r;
+}
+// _lerp(a, b, t): diff in float32, products/sums in float64, second form when t >= 0.5.
+D2PC_HD double lerp_percentile(float a, float b, double g) {
+  float diff = b - a;
+  double r = (double)a + (double)diff * g;
+  if (g >= 0.5) r = (double)b - (double)diff * (1.0 - g);
+  return r;
+}
+#define D2PC_Q02 (2.0 / 100.0)
+#define D2PC_Q98 (98.0 / 100.0)
+
+// a2  np.nanmedian of float32 values given the middle order statistic(s) (app.py:195)
+D2PC_HD float median_from_ranks(float lo, float hi, uint32_t count) {
+  if (count == 0) return nan_f32();
+  if (count & 1u) return hi;  // caller passes lo == hi == s[count/2]
+  float s = lo + hi;          // float32 sum, then float32 halving (np.mean of two float32)
+  return s / 2.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3/a4 per-frame normalisation parameters (app.py:197-204)
+// ---------------------------------------------------------------------------------------------
+struct NormParams {  // what the emit kernel needs, one per frame
+  double p2, p98, den, inv_den;
+  float lo32, hi32, den32, median;
+  int32_t branch;
+  int32_t has_nonfinite;
+};
+
+// p2/p98: interpolated percentiles (float64); vmin/vmax: min/max of the repaired float32 map.
+// any_nan: the repaired map still contains NaN (median itself was NaN) -> np.percentile is NaN.
+D2PC_HD void finalise_norm(double p2, double p98, float vmin, float vmax, bool any_nan,
+                           NormParams *o) {
+  int32_t branch = D2PC_BRANCH_PCT;
+  if (any_nan) {
+    p2 = p98 = (double)nan_f32();
+    // `p98 <= p2` is False for NaN, so the min/max fallback is not taken; `p98 > p2` is False
+    branch = D2PC_BRANCH_ZEROS;
+  } else if (p98 <= p2) {
+    p2 = (double)vmin;  // float(d.min()), float(d.max())
+    p98 = (double)vmax;
+    branch = (p98 > p2) ? D2PC_BRANCH_MINMAX : D2PC_BRANCH_ZEROS;
+  } else if (!(p98 > p2)) {
+    branch = D2PC_BRANCH_ZEROS;
+  }
+  o->p2 = p2;
+  o->p98 = p98;
+  o->den = (p98 - p2) + 1e-6;
+  o->inv_den = 1.0 / o->den;
+  o->lo32 = (float)p2;
+  o->hi32 = (float)p98;
+  o->den32 = (float)o->den;  // np.float32(p98 - p2 + 1e-6): python float -> float32 once
+  o->branch = branch;
+}
+
+// ---------------------------------------------------------------------------------------------
+// correctly rounded a / b for a divisor b whose correctly rounded reciprocal y = RN(1/b) is known
+// ---------------------------------------------------------------------------------------------
+// q0 = RN(a*y) is within 1.5 ulp of a/b; one FMA residual step makes it faithful; Markstein's
+// theorem (final-step lemma: y = RN(1/b), q faithful, r = a - b*q exact => RN(q + r*y) = RN(a/b))
+// makes the second step correctly rounded.  Valid for finite a, normal b, quotient and residuals
+// in the normal range (always true here: |a| in [2^-160, 2^130], b >= 1e-6); a == 0 -> 0;
+// non-finite or out-of-range cases fall back to the IEEE division.
+D2PC_HD double div_by_const(double a, double b, double y) {
+  double q0 = a * y;
+  double r0 = fma(-b, q0, a);
+  double q1 = fma(r0, y, q0);
+  double r1 = fma(-b, q1, a);
+  double q2 = fma(r1, y, q1);
+  // guard: anything exotic (inf/NaN operands, overflow, deep underflow) -> plain division
+  double aq = fabs(q2);
+  if (!(aq < 1e300) || (aq < 1e-290 && a != 0.0)) return a / b;
+  return q2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2 + a4 + a5 + a9  one pixel: raw (resized) depth -> xyz (app.py:193-206, 231-237)
+// ---------------------------------------------------------------------------------------------
+struct PixelConsts {  // per-call constants
+  double scale;       // float(depth_scale)
+  double cx, cy, f, inv_f;
+  int32_t invert;
+};
+
+// normalised depth as the double the loop sees: float(d[v,u])
+D2PC_HD double normalised_depth(float raw, const NormParams &np_, int32_t invert) {
+  float d = raw;
+  if (np_.has_nonfinite && !is_finite_f32(d)) d = np_.median;  // np.where(finite, d, med)
+  double n;
+  if (np_.branch == D2PC_BRANCH_PCT) {
+    double c = (double)d;
+    c = (c < np_.p2) ? np_.p2 : c;    // np.clip = minimum(maximum(d, p2), p98); d is not NaN here
+    c = (c > np_.p98) ? np_.p98 : c;
+    n = div_by_const(c - np_.p2, np_.den, np_.inv_den);
+    if (invert) n = 1.0 - n;
+  } else if (np_.branch == D2PC_BRANCH_MINMAX) {
+    float c = d;
+    c = (c < np_.lo32) ? np_.lo32 : c;
+    c = (c > np_.hi32) ? np_.hi32 : c;
+    float m = (c - np_.lo32) / np_.den32;  // float32 chain (python floats are weak scalars)
+    if (invert) m = 1.0f - m;
+    n = (double)m;
+  } else {
+    float m = 0.0f;
+    if (invert) m = 1.0f - m;
+    n = (double)m;
+  }
+  return n;
+}
+
+// u, v are pixel coordinates; out[0..2] = float32(x, y, z)
+D2PC_HD void back_project(double n, int32_t u, int32_t v, const PixelConsts &pc, float *x, float *y,
+                          float *z) {
+  double zd = n * pc.scale;                 // z = float(d[v,u]) * float(depth_scale)
+  double zz = (zd != 0.0) ? zd : 1e-6;      // (z if z != 0.0 else 1e-6)
+  double ax = ((double)u - pc.cx) * zz;     // (u - cx) * zz      (rounded)
+  double ay = ((double)v - pc.cy) * zz;
+  *x = (float)div_by_const(ax, pc.f, pc.inv_f);  // ... / f   (rounded), then np.float32
+  *y = (float)div_by_const(ay, pc.f, pc.inv_f);
+  *z = (float)zd;
+}
+
+}  // namespace d2pc
+#endif  // D2PC_MATH_H_

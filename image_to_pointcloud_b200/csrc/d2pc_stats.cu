@@ -1,0 +1,625 @@
+// d2pc_stats.cu -- reference steps a1..a5 (backend/app.py:186-206) on the device:
+// exact 2nd/98th-percentile order statistics of every frame's (virtually resized) depth map,
+// non-finite repair (np.nanmedian) and the frame's normalisation parameters.
+//
+// Fast path (3 launches per batch, depth map read from HBM exactly once):
+//   sample_kernel  1 CTA/frame   stratified sample -> bitonic sort in smem -> key brackets
+//                                [L, U] that contain the wanted ranks with ~6 sigma margin
+//   scan_kernel    streaming     per key: count below / equal-to-bound, append the few keys
+//                                strictly inside a bracket (about 2% each) to a candidate list,
+//                                min/max, non-finite counts.  Pure compares, no histogram:
+//                                the only atomics are per CTA.
+//   select_kernel  2 CTA/frame   exact rank selection inside the candidate list (direct smem
+//                                sort, or a second sample/bracket level for long lists), then
+//                                the last CTA of a frame evaluates NumPy's _lerp in float64
+//                                and writes the parameter block.
+// Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, candidate
+// overflow) are only marked; d2pc_stats_fallback_enqueue runs the input-agnostic exact path
+// (8-bit radix select, nanmedian repair) for those.
+#include "d2pc_device.cuh"
+
+namespace d2pc {
+
+__device__ __forceinline__ int32_t bracket_margin(double q, int S) {
+  double sd = sqrt((double)S * q * (1.0 - q));
+  return (int32_t)ceil(6.0 * sd) + 4;
+}
+
+// ------------------------------------------------------------------------------------------
+// sample_kernel
+// ------------------------------------------------------------------------------------------
+template <bool NATIVE>
+__global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
+  extern __shared__ uint32_t skeys[];
+  __shared__ uint32_t s_bad;
+  const int b = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  const uint32_t n = kp.g.P;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_bad = 0;
+    for (int i = 0; i < 2; ++i) {
+      fs->below[i] = 0; fs->eqL[i] = 0; fs->inside[i] = 0; fs->eqU[i] = 0;
+    }
+    fs->n_nonfinite = 0; fs->n_nan = 0;
+    fs->min_key = 0xFFFFFFFFu; fs->max_key = 0u;
+    for (int i = 0; i < 4; ++i) fs->sel_key[i] = 0;
+    fs->sel_fail = 0; fs->sel_done = 0;
+    fs->status = D2PC_FRAME_PENDING;
+    fs->fb_active = 0; fs->fb_any_nan = 0;
+    fs->norm.has_nonfinite = 0;
+    fs->norm.median = 0.0f;
+  }
+  if (n <= (uint32_t)kSortCap) {  // small frame: every finite key is a candidate
+    if (tid == 0) {
+      fs->brL[0] = fs->brL[1] = 0u;
+      fs->brU[0] = fs->brU[1] = 0xFFFFFFFFu;
+      fs->sample_ok = 1;
+    }
+    return;
+  }
+  __syncthreads();
+  const uint32_t S = kSampleSize;
+  for (uint32_t j = tid; j < S; j += blockDim.x) {
+    uint32_t start = (uint32_t)(((unsigned long long)j * n) / S);
+    uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * n) / S);
+    uint32_t width = end - start;
+    uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)b * 0x85EBCA6Bu + 12345u) % width;
+    float v = depth_at<NATIVE>(frame, kp.g, idx);
+    uint32_t key = 0xFFFFFFFFu;
+    if (is_finite_f32(v)) key = float_to_key(v); else atomicOr(&s_bad, 1u);
+    skeys[j] = key;
+  }
+  __syncthreads();
+  block_bitonic_sort(skeys, S);
+  if (tid < 2) {
+    const int br = tid;
+    const double q = br ? D2PC_Q98 : D2PC_Q02;
+    RankPair rp = percentile_ranks(n, q);
+    long long i_lo = (long long)(((unsigned long long)rp.lo * S) / n);
+    long long i_hi = (long long)(((unsigned long long)rp.hi * S) / n) + 1;
+    int32_t m = bracket_margin(q, (int)S);
+    long long iL = i_lo - m, iU = i_hi + m;
+    fs->brL[br] = iL < 0 ? 0u : skeys[iL];
+    fs->brU[br] = iU >= (long long)S ? 0xFFFFFFFFu : skeys[iU];
+  }
+  if (tid == 0) fs->sample_ok = s_bad ? 0u : 1u;
+}
+
+// ------------------------------------------------------------------------------------------
+// scan_kernel
+// ------------------------------------------------------------------------------------------
+struct ScanAcc {
+  uint32_t below[2], eqL[2], eqU[2], nf, nan, mn, mx;
+};
+
+__device__ __forceinline__ void scan_value(float v, const uint32_t L[2], const uint32_t U[2],
+                                           ScanAcc &a, uint32_t (*s_cand)[kScanTile],
+                                           uint32_t *s_cnt) {
+  uint32_t bits = f32_bits(v);
+  if ((bits & 0x7F800000u) == 0x7F800000u) {
+    a.nf++;
+    if (bits & 0x007FFFFFu) a.nan++;
+    return;
+  }
+  uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  a.mn = min(a.mn, key);
+  a.mx = max(a.mx, key);
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    if (key < L[br]) a.below[br]++;
+    else if (key == L[br]) a.eqL[br]++;
+    else if (key < U[br]) {
+      uint32_t pos = atomicAdd(&s_cnt[br], 1u);
+      s_cand[br][pos] = key;
+    } else if (key == U[br]) a.eqU[br]++;
+  }
+}
+
+template <bool NATIVE>
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_ok) {
+  __shared__ uint32_t s_cand[2][kScanTile];
+  __shared__ uint32_t s_cnt[2];
+  __shared__ uint32_t s_base[2];
+  __shared__ uint32_t s_red[10][kScanThreads / 32];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  const uint32_t n = kp.g.P;
+  uint32_t L[2], U[2];
+  L[0] = fs->brL[0]; L[1] = fs->brL[1]; U[0] = fs->brU[0]; U[1] = fs->brU[1];
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+  ScanAcc a;
+  a.below[0] = a.below[1] = a.eqL[0] = a.eqL[1] = a.eqU[0] = a.eqU[1] = 0;
+  a.nf = a.nan = 0; a.mn = 0xFFFFFFFFu; a.mx = 0u;
+  const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
+
+  if (NATIVE) {
+    float4 r[kScanPerThread / 4];
+    bool full[kScanPerThread / 4];
+#pragma unroll
+    for (int j = 0; j < kScanPerThread / 4; ++j) {
+      uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
+      full[j] = vec_ok && (p + 3u < n);
+      if (full[j]) r[j] = ldg_stream_f4(frame + p);
+    }
+#pragma unroll
+    for (int j = 0; j < kScanPerThread / 4; ++j) {
+      uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
+      if (full[j]) {
+        scan_value(r[j].x, L, U, a, s_cand, s_cnt);
+        scan_value(r[j].y, L, U, a, s_cand, s_cnt);
+        scan_value(r[j].z, L, U, a, s_cand, s_cnt);
+        scan_value(r[j].w, L, U, a, s_cand, s_cnt);
+      } else {
+        for (uint32_t k = 0; k < 4u; ++k)
+          if (p + k < n) scan_value(__ldg(frame + p + k), L, U, a, s_cand, s_cnt);
+      }
+    }
+  } else {
+    const uint32_t W = (uint32_t)kp.g.W;
+#pragma unroll 1
+    for (int j = 0; j < kScanPerThread / 4; ++j) {
+      uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
+      if (p >= n) continue;
+      uint32_t v = p / W;
+      uint32_t u = p - v * W;
+      AxisTap ty = axis_tap((int32_t)v, kp.g.scale_y, kp.g.h);
+      for (uint32_t k = 0; k < 4u && p + k < n; ++k) {
+        if (u >= W) {
+          u -= W;
+          v += 1;
+          ty = axis_tap((int32_t)v, kp.g.scale_y, kp.g.h);
+        }
+        AxisTap tx = axis_tap((int32_t)u, kp.g.scale_x, kp.g.w);
+        scan_value(bilinear_sample(frame, kp.g.w, tx, ty), L, U, a, s_cand, s_cnt);
+        u += 1;
+      }
+    }
+  }
+
+  // CTA reduction of the ten counters, then one global atomic each
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t vals[10] = {a.below[0], a.below[1], a.eqL[0], a.eqL[1], a.eqU[0], a.eqU[1], a.nf, a.nan, a.mn, a.mx};
+#pragma unroll
+  for (int c = 0; c < 10; ++c) {
+    uint32_t r = (c == 8) ? warp_min(vals[c]) : (c == 9) ? warp_max(vals[c]) : warp_sum(vals[c]);
+    if (lane == 0) s_red[c][warp] = r;
+  }
+  __syncthreads();
+  if (tid < 10) {
+    uint32_t r = s_red[tid][0];
+    for (int w = 1; w < kScanThreads / 32; ++w) {
+      uint32_t x = s_red[tid][w];
+      r = (tid == 8) ? min(r, x) : (tid == 9) ? max(r, x) : r + x;
+    }
+    switch (tid) {
+      case 0: if (r) atomicAdd(&fs->below[0], r); break;
+      case 1: if (r) atomicAdd(&fs->below[1], r); break;
+      case 2: if (r) atomicAdd(&fs->eqL[0], r); break;
+      case 3: if (r) atomicAdd(&fs->eqL[1], r); break;
+      case 4: if (r) atomicAdd(&fs->eqU[0], r); break;
+      case 5: if (r) atomicAdd(&fs->eqU[1], r); break;
+      case 6: if (r) atomicAdd(&fs->n_nonfinite, r); break;
+      case 7: if (r) atomicAdd(&fs->n_nan, r); break;
+      case 8: if (r != 0xFFFFFFFFu) atomicMin(&fs->min_key, r); break;
+      case 9: if (r != 0u) atomicMax(&fs->max_key, r); break;
+    }
+  }
+  // flush this tile's candidates: one reservation per bracket per CTA
+  if (tid < 2) {
+    uint32_t c = s_cnt[tid];
+    s_base[tid] = c ? atomicAdd(&fs->inside[tid], c) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const uint32_t c = s_cnt[br], base = s_base[br];
+    uint32_t *dst = kp.cand + ((size_t)b * 2 + br) * kp.cand_cap;
+    for (uint32_t i = tid; i < c; i += kScanThreads)
+      if (base + i < kp.cand_cap) dst[base + i] = s_cand[br][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// select_kernel
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+__device__ void finalise_fast(FrameState *fs, uint32_t n) {
+  volatile FrameState *vfs = fs;
+  if (vfs->sel_fail) {
+    vfs->status = D2PC_FRAME_NEEDS_FALLBACK;
+    return;
+  }
+  RankPair r2 = percentile_ranks(n, D2PC_Q02), r98 = percentile_ranks(n, D2PC_Q98);
+  double p2 = lerp_percentile(key_to_float(vfs->sel_key[0]), key_to_float(vfs->sel_key[1]), r2.gamma);
+  double p98 = lerp_percentile(key_to_float(vfs->sel_key[2]), key_to_float(vfs->sel_key[3]), r98.gamma);
+  NormParams np_;
+  finalise_norm(p2, p98, key_to_float(vfs->min_key), key_to_float(vfs->max_key), false, &np_);
+  np_.median = 0.0f;
+  np_.has_nonfinite = 0;
+  fs->norm = np_;
+  __threadfence();
+  vfs->status = D2PC_FRAME_READY;
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
+  extern __shared__ uint32_t sk[];  // kSortCap keys
+  __shared__ uint32_t s_n2, s_below2, s_L2, s_U2;
+  const int br = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  const uint32_t n = kp.g.P;
+  const uint32_t cap = kp.cand_cap;
+  const uint32_t *cand = kp.cand + ((size_t)b * 2 + br) * cap;
+  const uint32_t below = fs->below[br], eqL = fs->eqL[br], nin = fs->inside[br], eqU = fs->eqU[br];
+  const uint32_t L = fs->brL[br], U = fs->brU[br];
+  bool fail = (fs->n_nonfinite != 0u) || (fs->sample_ok == 0u) || (kp.force_fallback != 0);
+  RankPair rp = percentile_ranks(n, br ? D2PC_Q98 : D2PC_Q02);
+  long long need[2] = {-1, -1};
+  uint32_t key[2] = {0u, 0u};
+  for (int t = 0; t < 2; ++t) {
+    uint32_t r = t ? rp.hi : rp.lo;
+    if (r < below) { fail = true; continue; }
+    uint32_t r1 = r - below;
+    if (r1 < eqL) { key[t] = L; continue; }
+    uint32_t r2 = r1 - eqL;
+    if (r2 < nin) { need[t] = r2; continue; }
+    uint32_t r3 = r2 - nin;
+    if (r3 < eqU) { key[t] = U; continue; }
+    fail = true;
+  }
+  const bool any_need = need[0] >= 0 || need[1] >= 0;
+  if (nin > cap && any_need) fail = true;
+
+  if (!fail && any_need) {
+    if (nin <= (uint32_t)kSortCap) {
+      const uint32_t np2 = next_pow2(nin < 2u ? 2u : nin);
+      for (uint32_t i = tid; i < np2; i += blockDim.x) sk[i] = i < nin ? cand[i] : 0xFFFFFFFFu;
+      __syncthreads();
+      block_bitonic_sort(sk, np2);
+      for (int t = 0; t < 2; ++t)
+        if (need[t] >= 0) key[t] = sk[need[t]];
+    } else {
+      // level 2: sample the candidate list, bracket the wanted ranks, collect, sort
+      const uint32_t S2 = kSample2Size;
+      for (uint32_t j = tid; j < S2; j += blockDim.x) {
+        uint32_t start = (uint32_t)(((unsigned long long)j * nin) / S2);
+        uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * nin) / S2);
+        uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)(b * 2 + br) * 0xC2B2AE35u + 99u) % (end - start);
+        sk[j] = cand[idx];
+      }
+      if (tid == 0) { s_n2 = 0; s_below2 = 0; }
+      __syncthreads();
+      block_bitonic_sort(sk, S2);
+      long long rlo = need[0] >= 0 ? need[0] : need[1];
+      long long rhi = need[1] >= 0 ? need[1] : need[0];
+      if (tid == 0) {
+        double q2 = (double)rlo / (double)nin;
+        int32_t m2 = bracket_margin(q2, (int)S2);
+        long long iL = (long long)(((unsigned long long)rlo * S2) / nin) - m2;
+        long long iU = (long long)(((unsigned long long)rhi * S2) / nin) + 1 + m2;
+        s_L2 = iL < 0 ? 0u : sk[iL];
+        s_U2 = iU >= (long long)S2 ? 0xFFFFFFFFu : sk[iU];
+      }
+      __syncthreads();
+      const uint32_t L2 = s_L2, U2 = s_U2;
+      uint32_t my_below = 0;
+      for (uint32_t i = tid; i < nin; i += blockDim.x) {
+        uint32_t k = cand[i];
+        if (k < L2) my_below++;
+        else if (k <= U2) {
+          uint32_t pos = atomicAdd(&s_n2, 1u);
+          if (pos < (uint32_t)kSortCap) sk[pos] = k;
+        }
+      }
+      my_below = warp_sum(my_below);
+      if ((tid & 31) == 0 && my_below) atomicAdd(&s_below2, my_below);
+      __syncthreads();
+      const uint32_t n2 = s_n2, below2 = s_below2;
+      if (n2 > (uint32_t)kSortCap || (uint32_t)rlo < below2 || (uint32_t)rhi >= below2 + n2) {
+        fail = true;
+      } else {
+        const uint32_t np2 = next_pow2(n2 < 2u ? 2u : n2);
+        for (uint32_t i = n2 + tid; i < np2; i += blockDim.x) sk[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        block_bitonic_sort(sk, np2);
+        for (int t = 0; t < 2; ++t)
+          if (need[t] >= 0) key[t] = sk[need[t] - below2];
+      }
+    }
+  }
+
+  if (tid == 0) {
+    fs->sel_key[2 * br + 0] = key[0];
+    fs->sel_key[2 * br + 1] = key[1];
+    if (fail) atomicOr(&fs->sel_fail, 1u);
+    __threadfence();
+    uint32_t ticket = atomicAdd(&fs->sel_done, 1u);
+    if (ticket == 1u) {
+      __threadfence();
+      finalise_fast(fs, n);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fallback: exact 8-bit radix select over the whole map for flagged frames
+// ------------------------------------------------------------------------------------------
+enum { kStageMedian = 0, kStagePercentile = 1 };
+
+__global__ void fb_begin_kernel(KParams kp) {
+  const int b = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  uint32_t *hist = kp.fb_hist + (size_t)b * kFbTargets * 256;
+  for (int i = threadIdx.x; i < kFbTargets * 256; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x != 0) return;
+  fs->fb_active = 0;
+  fs->fb_any_nan = 0;
+  if (fs->status != D2PC_FRAME_NEEDS_FALLBACK) return;
+  if (fs->n_nonfinite == 0) return;  // no repair needed: median stage idle
+  const uint32_t m = kp.g.P - fs->n_nan;  // np.nanmedian drops NaN, keeps +-inf
+  if (m == 0) return;
+  for (int t = 0; t < kFbTargets; ++t) fs->fb_prefix[t] = 0;
+  if (m & 1u) {
+    fs->fb_rank[0] = m / 2;
+    fs->fb_active = 1;
+  } else {
+    fs->fb_rank[0] = m / 2 - 1;
+    fs->fb_rank[1] = m / 2;
+    fs->fb_active = 2;
+  }
+}
+
+template <bool NATIVE>
+__global__ void __launch_bounds__(kScanThreads) fb_hist_kernel(KParams kp, int stage, int pass) {
+  __shared__ uint32_t sh[kFbTargets][256];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_NEEDS_FALLBACK) return;
+  const int T = (int)fs->fb_active;
+  if (T == 0) return;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  const uint32_t n = kp.g.P;
+  for (int i = tid; i < kFbTargets * 256; i += kScanThreads) (&sh[0][0])[i] = 0;
+  uint32_t prefix[kFbTargets];
+  for (int t = 0; t < kFbTargets; ++t) prefix[t] = fs->fb_prefix[t];
+  const float med = fs->norm.median;
+  __syncthreads();
+  const int shift = 24 - 8 * pass;
+  const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
+  for (int j = 0; j < kScanPerThread; ++j) {
+    uint32_t p = tile_base + (uint32_t)(j * kScanThreads + tid);
+    if (p >= n) break;
+    float v = depth_at<NATIVE>(frame, kp.g, p);
+    if (stage == kStageMedian) {
+      if (is_nan_f32(v)) continue;
+    } else {
+      if (!is_finite_f32(v)) v = med;  // np.where(finite, d, med)
+    }
+    uint32_t key = float_to_key(v);
+    for (int t = 0; t < T; ++t) {
+      bool match = (pass == 0) || ((key >> (shift + 8)) == (prefix[t] >> (shift + 8)));
+      if (match) atomicAdd(&sh[t][(key >> shift) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t *hist = kp.fb_hist + (size_t)b * kFbTargets * 256;
+  for (int i = tid; i < T * 256; i += kScanThreads) {
+    uint32_t c = (&sh[0][0])[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+__global__ void fb_pick_kernel(KParams kp, int pass) {
+  const int b = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  uint32_t *hist = kp.fb_hist + (size_t)b * kFbTargets * 256;
+  const bool live = fs->status == D2PC_FRAME_NEEDS_FALLBACK && fs->fb_active > 0;
+  if (live && threadIdx.x < fs->fb_active) {
+    const int t = threadIdx.x;
+    const int shift = 24 - 8 * pass;
+    uint32_t rank = fs->fb_rank[t], cum = 0;
+    int d = 0;
+    for (; d < 256; ++d) {
+      uint32_t c = hist[t * 256 + d];
+      if (rank < cum + c) break;
+      cum += c;
+    }
+    if (d > 255) d = 255;  // cannot happen for a consistent rank; stay in range
+    fs->fb_prefix[t] |= (uint32_t)d << shift;
+    fs->fb_rank[t] = rank - cum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kFbTargets * 256; i += blockDim.x) hist[i] = 0;
+}
+
+// after the median stage: store the repair value, then arm the percentile stage
+__global__ void fb_median_kernel(KParams kp) {
+  const int b = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  if (threadIdx.x != 0 || fs->status != D2PC_FRAME_NEEDS_FALLBACK) return;
+  const uint32_t n = kp.g.P;
+  float med = 0.0f;
+  int has_nf = 0;
+  if (fs->n_nonfinite != 0) {
+    has_nf = 1;
+    const uint32_t m = n - fs->n_nan;
+    if (m == 0) {
+      med = nan_f32();
+    } else {
+      const int T = (int)fs->fb_active;
+      med = median_from_ranks(key_to_float(fs->fb_prefix[0]), key_to_float(fs->fb_prefix[T - 1]), m);
+    }
+  }
+  fs->norm.median = med;
+  fs->norm.has_nonfinite = has_nf;
+  const bool any_nan = has_nf && is_nan_f32(med);
+  fs->fb_any_nan = any_nan ? 1u : 0u;
+  if (any_nan) {
+    fs->fb_active = 0;
+    return;
+  }
+  RankPair r2 = percentile_ranks(n, D2PC_Q02), r98 = percentile_ranks(n, D2PC_Q98);
+  fs->fb_rank[0] = r2.lo; fs->fb_rank[1] = r2.hi; fs->fb_rank[2] = r98.lo; fs->fb_rank[3] = r98.hi;
+  for (int t = 0; t < kFbTargets; ++t) fs->fb_prefix[t] = 0;
+  fs->fb_active = 4;
+}
+
+__global__ void fb_finalise_kernel(KParams kp) {
+  const int b = blockIdx.x;
+  FrameState *fs = kp.state + b;
+  if (threadIdx.x != 0 || fs->status != D2PC_FRAME_NEEDS_FALLBACK) return;
+  const uint32_t n = kp.g.P;
+  NormParams np_;
+  const float med = fs->norm.median;
+  const int has_nf = fs->norm.has_nonfinite;
+  if (fs->fb_any_nan) {
+    finalise_norm(0.0, 0.0, 0.0f, 0.0f, true, &np_);
+  } else {
+    RankPair r2 = percentile_ranks(n, D2PC_Q02), r98 = percentile_ranks(n, D2PC_Q98);
+    double p2 = lerp_percentile(key_to_float(fs->fb_prefix[0]), key_to_float(fs->fb_prefix[1]), r2.gamma);
+    double p98 = lerp_percentile(key_to_float(fs->fb_prefix[2]), key_to_float(fs->fb_prefix[3]), r98.gamma);
+    uint32_t kmin = fs->min_key, kmax = fs->max_key;  // over finite values (0xFFFFFFFF / 0: none)
+    if (has_nf) {
+      uint32_t km = float_to_key(med);
+      kmin = min(kmin, km);
+      kmax = max(kmax, km);
+    }
+    finalise_norm(p2, p98, key_to_float(kmin), key_to_float(kmax), false, &np_);
+  }
+  np_.median = med;
+  np_.has_nonfinite = has_nf;
+  fs->norm = np_;
+  __threadfence();
+  fs->status = D2PC_FRAME_READY;
+}
+
+// ------------------------------------------------------------------------------------------
+// status / parameter export
+// ------------------------------------------------------------------------------------------
+__global__ void status_kernel(KParams kp, int32_t *d_status, int32_t *d_any) {
+  __shared__ int s_any;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < kp.batch; b += blockDim.x) {
+    int32_t s = kp.state[b].status;
+    if (d_status) d_status[b] = s;
+    if (s == D2PC_FRAME_NEEDS_FALLBACK) s_any = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && d_any) *d_any = s_any;
+}
+
+__global__ void params_kernel(KParams kp, D2pcFrameParams *out) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < kp.batch; b += gridDim.x * blockDim.x) {
+    const FrameState &fs = kp.state[b];
+    D2pcFrameParams o;
+    o.p2 = fs.norm.p2; o.p98 = fs.norm.p98; o.den = fs.norm.den; o.inv_den = fs.norm.inv_den;
+    o.lo32 = fs.norm.lo32; o.hi32 = fs.norm.hi32; o.den32 = fs.norm.den32; o.median = fs.norm.median;
+    o.branch = fs.norm.branch; o.status = fs.status;
+    o.n_nonfinite = fs.n_nonfinite; o.n_nan = fs.n_nan;
+    o.n_cand[0] = fs.inside[0]; o.n_cand[1] = fs.inside[1];
+    o.reserved[0] = fs.sel_fail; o.reserved[1] = fs.sample_ok;
+    out[b] = o;
+  }
+}
+
+}  // namespace d2pc
+
+using namespace d2pc;
+
+static int check_ws(const D2pcConfig *cfg, const void *ws, size_t ws_bytes) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!ws) return D2PC_ERR_INVALID_ARGUMENT;
+  if (ws_bytes < make_layout(*cfg).total) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+  if (((uintptr_t)ws & 255u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
+  return D2PC_OK;
+}
+
+extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
+                                  size_t workspace_bytes, void *stream) {
+  int rc = check_ws(cfg, d_workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  const size_t sample_smem = (size_t)kSampleSize * sizeof(uint32_t);
+  const size_t select_smem = (size_t)kSortCap * sizeof(uint32_t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem);
+    if (e != cudaSuccess) return record_cuda_error(e);
+    attr_done = true;
+  }
+  const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)d_depth & 15u) == 0u);
+  dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
+  if (kp.g.native) {
+    sample_kernel<true><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
+    D2PC_CHECK_LAUNCH();
+    scan_kernel<true><<<scan_grid, kScanThreads, 0, st>>>(kp, vec_ok);
+  } else {
+    sample_kernel<false><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
+    D2PC_CHECK_LAUNCH();
+    scan_kernel<false><<<scan_grid, kScanThreads, 0, st>>>(kp, 0);
+  }
+  D2PC_CHECK_LAUNCH();
+  select_kernel<<<dim3(2, cfg->batch), kSelThreads, select_smem, st>>>(kp);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
+extern "C" int d2pc_stats_fallback_enqueue(const D2pcConfig *cfg, const float *d_depth,
+                                           void *d_workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_ws(cfg, d_workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  dim3 grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
+  fb_begin_kernel<<<cfg->batch, 256, 0, st>>>(kp);
+  D2PC_CHECK_LAUNCH();
+  for (int stage = 0; stage < 2; ++stage) {
+    for (int pass = 0; pass < 4; ++pass) {
+      if (kp.g.native) fb_hist_kernel<true><<<grid, kScanThreads, 0, st>>>(kp, stage, pass);
+      else fb_hist_kernel<false><<<grid, kScanThreads, 0, st>>>(kp, stage, pass);
+      D2PC_CHECK_LAUNCH();
+      fb_pick_kernel<<<cfg->batch, 256, 0, st>>>(kp, pass);
+      D2PC_CHECK_LAUNCH();
+    }
+    if (stage == 0) fb_median_kernel<<<cfg->batch, 32, 0, st>>>(kp);
+    else fb_finalise_kernel<<<cfg->batch, 32, 0, st>>>(kp);
+    D2PC_CHECK_LAUNCH();
+  }
+  return D2PC_OK;
+}
+
+extern "C" int d2pc_frame_status(const D2pcConfig *cfg, const void *d_workspace, int32_t *d_status,
+                                 int32_t *d_any_fallback, void *stream) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!d_workspace) return D2PC_ERR_INVALID_ARGUMENT;
+  KParams kp = make_kparams(*cfg, nullptr, (void *)d_workspace);
+  status_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(kp, d_status, d_any_fallback);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
+extern "C" int d2pc_frame_params(const D2pcConfig *cfg, const void *d_workspace,
+                                 D2pcFrameParams *d_params, void *stream) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!d_workspace || !d_params) return D2PC_ERR_INVALID_ARGUMENT;
+  KParams kp = make_kparams(*cfg, nullptr, (void *)d_workspace);
+  params_kernel<<<(cfg->batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kp, d_params);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}

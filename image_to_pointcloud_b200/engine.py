@@ -1,0 +1,227 @@
+"""FrameEngine -- host side of the B200 depth-map -> point-cloud stage.
+
+Owns the device workspace for one geometry (image size, depth size, batch) on one GPU and drives
+the C-ABI library (include/d2pc.h) on a CUDA stream.  PyTorch is used only as the container for
+device / pinned memory and for streams; every computation happens in libd2pc.so.  There is no CPU
+or eager fallback: constructing an engine without a CUDA device or without the library raises.
+
+A *frame* is one (image, depth) pair; a call processes ``batch`` frames that share geometry and
+knobs.  Frames are independent (the reference function is pure, backend/app.py:174-250), which is
+also how work is sharded across GPUs (see ``shard_frames``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import D2pcConfig, D2pcFrameParams, check
+
+DENSITY_STEP = {"low": 4, "medium": 2, "high": 1}  # reference backend/app.py:226
+
+
+def reference_intrinsics(img_w: int, img_h: int, fov: Optional[float]) -> Tuple[float, float, float]:
+    """cx, cy, f exactly as the reference computes them (backend/app.py:219-223)."""
+    cx, cy = img_w / 2.0, img_h / 2.0
+    if fov and fov > 0:
+        f = (img_w / 2.0) / np.tan(np.deg2rad(fov) / 2.0)
+    else:
+        f = max(img_w, img_h) * 1.2
+    return float(cx), float(cy), float(f)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class EmitResult:
+    xyz: torch.Tensor      # float32 [batch, N, 3] (device); rows [0, count[b]) valid per frame
+    rgb: torch.Tensor      # float32 [batch, N, 3]
+    count: torch.Tensor    # int32   [batch]
+    bounds: Optional[torch.Tensor]  # float32 [batch, 6] or None
+
+
+class FrameEngine:
+    def __init__(self, img_h: int, img_w: int, dep_h: Optional[int] = None, dep_w: Optional[int] = None,
+                 *, batch: int = 1, img_c: int = 3, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("image_to_pointcloud_b200 needs a CUDA device (no CPU fallback exists)")
+        self.lib = _lib.load_library()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("FrameEngine device must be a CUDA device")
+        self.img_h, self.img_w, self.img_c = int(img_h), int(img_w), int(img_c)
+        self.dep_h = int(dep_h if dep_h is not None else img_h)
+        self.dep_w = int(dep_w if dep_w is not None else img_w)
+        self.batch = int(batch)
+        # workspace sized for the densest configuration (step 1) of this geometry
+        cfg = self.make_config(density="high")
+        nbytes = C.c_size_t(0)
+        check(self.lib.d2pc_workspace_bytes(C.byref(cfg), C.byref(nbytes)), "d2pc_workspace_bytes")
+        self.workspace_bytes = int(nbytes.value)
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+            self._status = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+            self._any = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._any_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        assert self.workspace.data_ptr() % 256 == 0
+        self._voxel_table = None
+
+    # ---- configuration -------------------------------------------------------------------
+    def make_config(self, density: str = "high", invert: bool = True, depth_scale: float = 10.0,
+                    fov: Optional[float] = None, z_range: Optional[Tuple[float, float]] = None,
+                    drop_nonfinite: bool = False, want_bounds: bool = False,
+                    force_fallback: bool = False) -> D2pcConfig:
+        step = DENSITY_STEP[density]  # KeyError for unknown densities, like the reference
+        cx, cy, f = reference_intrinsics(self.img_w, self.img_h, fov)
+        cfg = D2pcConfig()
+        cfg.batch = self.batch
+        cfg.img_h, cfg.img_w, cfg.img_c = self.img_h, self.img_w, self.img_c
+        cfg.dep_h, cfg.dep_w = self.dep_h, self.dep_w
+        cfg.step = step
+        cfg.invert = 1 if invert else 0
+        cfg.depth_scale = float(depth_scale)
+        cfg.cx, cfg.cy, cfg.f = cx, cy, f
+        if z_range is not None:
+            cfg.use_z_range = 1
+            cfg.z_min, cfg.z_max = float(np.float32(z_range[0])), float(np.float32(z_range[1]))
+        cfg.drop_nonfinite = 1 if drop_nonfinite else 0
+        cfg.want_bounds = 1 if want_bounds else 0
+        cfg.force_fallback = 1 if force_fallback else 0
+        return cfg
+
+    def points_per_frame(self, cfg: D2pcConfig) -> int:
+        s = cfg.step
+        return (-(-self.img_h // s)) * (-(-self.img_w // s))
+
+    def alloc_outputs(self, cfg: D2pcConfig):
+        n = self.points_per_frame(cfg)
+        with torch.cuda.device(self.device):
+            xyz = torch.empty((self.batch, n, 3), dtype=torch.float32, device=self.device)
+            rgb = torch.empty((self.batch, n, 3), dtype=torch.float32, device=self.device)
+        return xyz, rgb
+
+    # ---- checks --------------------------------------------------------------------------
+    def _check_inputs(self, depth: torch.Tensor, bgr: Optional[torch.Tensor]):
+        if depth.device != self.device or depth.dtype != torch.float32 or not depth.is_contiguous():
+            raise ValueError("depth must be a contiguous float32 tensor on the engine's device")
+        if tuple(depth.shape) != (self.batch, self.dep_h, self.dep_w):
+            raise ValueError(f"depth shape {tuple(depth.shape)} != {(self.batch, self.dep_h, self.dep_w)}")
+        if self.img_c >= 3:
+            if bgr is None or bgr.device != self.device or bgr.dtype != torch.uint8 or not bgr.is_contiguous():
+                raise ValueError("bgr must be a contiguous uint8 tensor on the engine's device")
+            if tuple(bgr.shape) != (self.batch, self.img_h, self.img_w, self.img_c):
+                raise ValueError(f"bgr shape {tuple(bgr.shape)} != {(self.batch, self.img_h, self.img_w, self.img_c)}")
+
+    def _stream(self, stream) -> int:
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return s.cuda_stream
+
+    # ---- asynchronous pieces (enqueue only, no host sync) ---------------------------------
+    def enqueue_stats(self, cfg: D2pcConfig, depth: torch.Tensor, stream=None) -> None:
+        check(self.lib.d2pc_stats_enqueue(C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
+                                          self.workspace_bytes, self._stream(stream)), "d2pc_stats_enqueue")
+
+    def enqueue_stats_fallback(self, cfg: D2pcConfig, depth: torch.Tensor, stream=None) -> None:
+        check(self.lib.d2pc_stats_fallback_enqueue(C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
+                                                   self.workspace_bytes, self._stream(stream)),
+              "d2pc_stats_fallback_enqueue")
+
+    def enqueue_status(self, cfg: D2pcConfig, stream=None) -> None:
+        """status words -> self._status, any-fallback flag -> pinned host word (async copy)."""
+        check(self.lib.d2pc_frame_status(C.byref(cfg), self.workspace.data_ptr(), self._status.data_ptr(),
+                                         self._any.data_ptr(), self._stream(stream)), "d2pc_frame_status")
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(s):
+            self._any_host.copy_(self._any, non_blocking=True)
+
+    def enqueue_emit(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],
+                     xyz: torch.Tensor, rgb: torch.Tensor, count: torch.Tensor,
+                     bounds: Optional[torch.Tensor] = None, stream=None) -> None:
+        check(self.lib.d2pc_emit_enqueue(C.byref(cfg), depth.data_ptr(), _ptr(bgr), self.workspace.data_ptr(),
+                                         self.workspace_bytes, xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(),
+                                         _ptr(bounds), self._stream(stream)), "d2pc_emit_enqueue")
+
+    # ---- whole path ----------------------------------------------------------------------
+    def process(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],
+                xyz: Optional[torch.Tensor] = None, rgb: Optional[torch.Tensor] = None,
+                count: Optional[torch.Tensor] = None, stream=None) -> EmitResult:
+        """stats -> emit for one device-resident batch; synchronises the stream once to learn
+        whether any frame needs the exact fallback, and if so runs it and re-emits those frames."""
+        self._check_inputs(depth, bgr)
+        if xyz is None or rgb is None:
+            xyz, rgb = self.alloc_outputs(cfg)
+        n = self.points_per_frame(cfg)
+        if tuple(xyz.shape) != (self.batch, n, 3) or tuple(rgb.shape) != (self.batch, n, 3):
+            raise ValueError("output tensors must be float32 [batch, N, 3]")
+        with torch.cuda.device(self.device):
+            if count is None:
+                count = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+            bounds = torch.empty((self.batch, 6), dtype=torch.float32, device=self.device) if cfg.want_bounds else None
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.enqueue_stats(cfg, depth, s)
+        self.enqueue_status(cfg, s)
+        self.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, bounds, s)
+        s.synchronize()
+        if int(self._any_host[0]) != 0:
+            self.enqueue_stats_fallback(cfg, depth, s)
+            self.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, bounds, s)
+            s.synchronize()
+        return EmitResult(xyz, rgb, count, bounds)
+
+    def frame_params(self, cfg: D2pcConfig):
+        """Per-frame normalisation parameters as the device computed them (tests / debugging)."""
+        with torch.cuda.device(self.device):
+            buf = torch.zeros(self.batch * C.sizeof(D2pcFrameParams), dtype=torch.uint8, device=self.device)
+        check(self.lib.d2pc_frame_params(C.byref(cfg), self.workspace.data_ptr(), buf.data_ptr(),
+                                         self._stream(None)), "d2pc_frame_params")
+        raw = buf.cpu().numpy().tobytes()
+        out = []
+        for b in range(self.batch):
+            p = D2pcFrameParams.from_buffer_copy(raw, b * C.sizeof(D2pcFrameParams))
+            out.append({k: (list(getattr(p, k)) if k in ("n_cand", "reserved") else getattr(p, k))
+                        for k, _ in D2pcFrameParams._fields_})
+        return out
+
+    # ---- ax-2 voxel grid ------------------------------------------------------------------
+    def voxel_downsample(self, cfg: D2pcConfig, res: EmitResult, voxel_size: float,
+                         want_index: bool = False, stream=None):
+        """Voxel-grid down-sampling of the emitted rows of every frame (needs cfg.want_bounds).
+        Returns (vox_xyz [B,N,3], vox_rgb [B,N,3], vox_idx [B,N,3] or None, vox_count [B])."""
+        if not cfg.want_bounds or res.bounds is None:
+            raise ValueError("voxel_downsample needs an emit with want_bounds=True")
+        if not voxel_size > 0:
+            raise ValueError("voxel_size <= 0.")
+        nbytes = C.c_size_t(0)
+        check(self.lib.d2pc_voxel_table_bytes(C.byref(cfg), C.byref(nbytes)), "d2pc_voxel_table_bytes")
+        with torch.cuda.device(self.device):
+            if self._voxel_table is None or self._voxel_table.numel() < nbytes.value:
+                self._voxel_table = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
+            vxyz = torch.empty_like(res.xyz)
+            vrgb = torch.empty_like(res.rgb)
+            vidx = torch.empty(res.xyz.shape, dtype=torch.int32, device=self.device) if want_index else None
+            vcount = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+            verr = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+        check(self.lib.d2pc_voxel_enqueue(C.byref(cfg), float(voxel_size), res.xyz.data_ptr(), res.rgb.data_ptr(),
+                                          res.count.data_ptr(), res.bounds.data_ptr(),
+                                          self._voxel_table.data_ptr(), self._voxel_table.numel(),
+                                          vxyz.data_ptr(), vrgb.data_ptr(), _ptr(vidx), vcount.data_ptr(),
+                                          verr.data_ptr(), self._stream(stream)), "d2pc_voxel_enqueue")
+        if bool((verr.cpu() != 0).any()):
+            raise ValueError("voxel_size is too small.")
+        return vxyz, vrgb, vidx, vcount
+
+
+def shard_frames(n_frames: int, world_size: int, rank: int) -> range:
+    """Contiguous block partition of frame indices over ranks (one rank per GPU, no collective:
+    frames are independent).  Blocks differ by at most one frame."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_frames, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))

@@ -1,0 +1,160 @@
+/*
+ * d2pc.h -- C ABI of libd2pc.so: the B200 (sm_100a) depth-map -> coloured point-cloud stage.
+ *
+ * What this replaces.  The reference has no FFI or plugin boundary for this path: the stage is
+ * one Python function, depth_to_point_cloud(image, depth, density, invert, depth_scale, smooth,
+ * smooth_ksize, fov) -> (points f32[N,3], colors f32[N,3])   (reference backend/app.py:174-250),
+ * called once per request at backend/app.py:468-476.  The drop-in is therefore a Python function
+ * of the same name and signature (image_to_pointcloud_b200.depth_to_point_cloud) that rebinds
+ * that name; the entry points below are what that function binds with ctypes, and what any
+ * other host (C, C++, cgo, JNI, N-API) would bind.  INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller
+ *    (torch tensors in the Python host), including the workspace.  The library allocates
+ *    nothing, keeps no global state and never synchronises the host: every call only enqueues
+ *    kernels on `stream` (a cudaStream_t passed as void*).  Re-entrant per (device, stream).
+ *  - return value: 0 = D2PC_OK, otherwise a D2PC_ERR_* code; nothing is thrown across the ABI.
+ *    d2pc_error_string() gives the text.  The Python host raises on non-zero, so the reference's
+ *    error convention (raise -> pipeline marks the job "error", app.py:248-250,561-565) holds.
+ *  - a "frame" is one (image, depth) pair.  A call processes `batch` frames that share geometry
+ *    and knobs; frames are independent (own percentiles, own output slot, no cross-frame state:
+ *    the reference function is pure), which is also the multi-GPU sharding unit.
+ *
+ * Reference step -> entry point
+ *   a1 resize (app.py:186-188), a2 non-finite repair (:191-196), a3 percentiles (:197-199),
+ *   a4 clip+normalise (:200-204), a5 invert (:205-206)       -> d2pc_stats_enqueue
+ *                                                               (+ d2pc_stats_fallback_enqueue)
+ *   a7 intrinsics (:216-223), a8 stride (:225-226)            -> D2pcConfig fields (host computes
+ *                                                               cx, cy, f exactly as the reference)
+ *   a9 back-projection (:228-237), a10 colour gather (:239-244),
+ *   a11 emission (:246), ax-1 depth-range mask + compaction   -> d2pc_emit_enqueue
+ *   ax-2 voxel-grid down-sampling (north-star extension)      -> d2pc_voxel_enqueue
+ */
+#ifndef D2PC_H_
+#define D2PC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2PC_ABI_VERSION 1
+
+enum {
+  D2PC_OK = 0,
+  D2PC_ERR_INVALID_ARGUMENT = 1, /* bad geometry / null pointer / unsupported knob          */
+  D2PC_ERR_WORKSPACE_TOO_SMALL = 2,
+  D2PC_ERR_CUDA = 3,             /* a CUDA runtime call or launch failed (see error_string)  */
+  D2PC_ERR_UNSUPPORTED = 4       /* valid reference input this build does not implement yet  */
+};
+
+/* per-frame status word written by the stats kernels (workspace, see d2pc_frame_status) */
+enum {
+  D2PC_FRAME_PENDING = 0,
+  D2PC_FRAME_READY = 1,          /* normalisation parameters are final; emit may run         */
+  D2PC_FRAME_NEEDS_FALLBACK = 2  /* fast selection declined (non-finite values, bracket miss,
+                                    candidate overflow): run d2pc_stats_fallback_enqueue     */
+};
+
+/* normalisation branch taken for a frame (reference app.py:197-204) */
+enum {
+  D2PC_BRANCH_PCT = 0,    /* p98 > p2: float64 clip/normalise chain                          */
+  D2PC_BRANCH_MINMAX = 1, /* percentiles degenerate, min < max: float32 chain                */
+  D2PC_BRANCH_ZEROS = 2   /* constant (or NaN-poisoned) map: d = 0                           */
+};
+
+/* Geometry and knobs shared by all frames of a call.  Plain old data, passed by pointer. */
+typedef struct D2pcConfig {
+  int32_t batch;        /* frames in this call (>= 1)                                        */
+  int32_t img_h, img_w; /* H, W of the image = size of the output grid                      */
+  int32_t img_c;        /* image channels: 3 or 4 (BGR / BGRA, app.py:240-242); 1 = grey ->
+                           colour [128,128,128] (app.py:243-244)                            */
+  int32_t dep_h, dep_w; /* h, w of the depth map; != (H, W) -> bilinear resize (app.py:187) */
+  int32_t step;         /* sampling stride: 4 / 2 / 1 for low / medium / high (app.py:226)  */
+  int32_t invert;       /* app.py:205                                                       */
+  double depth_scale;   /* app.py:233                                                       */
+  double cx, cy, f;     /* intrinsics, computed by the host as app.py:219-223               */
+  /* ax-1 depth-range mask (extension; off = keep every point like the reference) */
+  int32_t use_z_range;  /* 0 / 1                                                            */
+  float z_min, z_max;   /* keep iff z_min <= z32 <= z_max on the emitted float32 z          */
+  int32_t drop_nonfinite; /* 1: also drop points whose (resized) depth was NaN/inf          */
+  int32_t want_bounds;  /* 1: emit also reduces per-frame min/max of kept xyz (for voxels,
+                           LAS offsets app.py:352 and GIS bounds app.py:394-399)            */
+  int32_t force_fallback; /* test hook: 1 = stats marks every frame NEEDS_FALLBACK          */
+} D2pcConfig;
+
+/* Normalisation parameters of one frame as the device computed them (debug / tests). */
+typedef struct D2pcFrameParams {
+  double p2, p98;       /* the two scalars of app.py:197-199 (after the min/max fallback)    */
+  double den;           /* (p98 - p2) + 1e-6                                                 */
+  double inv_den;       /* correctly rounded 1/den                                           */
+  float lo32, hi32, den32; /* float32 operands of the MINMAX branch                         */
+  float median;         /* np.nanmedian replacement value (valid if n_nonfinite > 0)        */
+  int32_t branch;       /* D2PC_BRANCH_*                                                    */
+  int32_t status;       /* D2PC_FRAME_*                                                     */
+  uint32_t n_nonfinite; /* NaN or +-inf in the (resized) map                                */
+  uint32_t n_nan;
+  uint32_t n_cand[2];   /* candidates collected for the 2% / 98% brackets (fast path)       */
+  uint32_t reserved[2];
+} D2pcFrameParams;
+
+int d2pc_abi_version(void);
+const char *d2pc_error_string(int code);
+/* text of the last CUDA error seen by this thread inside the library ("" if none) */
+const char *d2pc_last_cuda_error(void);
+
+/* Bytes of workspace needed for cfg (depends on batch and geometry only). */
+int d2pc_workspace_bytes(const D2pcConfig *cfg, size_t *bytes);
+
+/* a1..a5: exact 2nd/98th percentile statistics of every frame's (virtually resized) depth map
+ * and the frame's normalisation parameters, entirely on the device.
+ *   d_depth  float32 [batch, dep_h, dep_w]
+ * Fast path: sample -> brackets -> one streaming pass (counts + candidates) -> exact select.
+ * Frames it cannot finish exactly are marked D2PC_FRAME_NEEDS_FALLBACK. */
+int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* Exact, input-agnostic selection (multi-pass radix select, nanmedian repair) for every frame
+ * whose status is NEEDS_FALLBACK; no-op kernels for the others. */
+int d2pc_stats_fallback_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
+                                size_t workspace_bytes, void *stream);
+
+/* Copies the per-frame status words (int32 [batch]) to a device buffer the host can read back
+ * with one small memcpy; d_any_fallback (int32 [1]) is set to 1 if any frame needs it. */
+int d2pc_frame_status(const D2pcConfig *cfg, const void *d_workspace, int32_t *d_status,
+                      int32_t *d_any_fallback, void *stream);
+
+/* Copies the per-frame parameter blocks to d_params (D2pcFrameParams [batch]). */
+int d2pc_frame_params(const D2pcConfig *cfg, const void *d_workspace, D2pcFrameParams *d_params,
+                      void *stream);
+
+/* a4..a11 (+ ax-1): fused resize / repair / normalise / invert / back-project / colour gather /
+ * mask / ordered compaction / packing.
+ *   d_bgr    uint8  [batch, H, W, img_c]           (may be NULL when img_c == 1)
+ *   d_xyz    float32 [batch, N, 3], d_rgb likewise, N = ceil(H/step) * ceil(W/step)
+ *   d_count  uint32 [batch]   rows emitted per frame (== N unless a mask is active)
+ *   d_bounds float32 [batch, 6] (min x,y,z, max x,y,z) if cfg->want_bounds, else may be NULL */
+int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
+                      void *d_workspace, size_t workspace_bytes, float *d_xyz, float *d_rgb,
+                      uint32_t *d_count, float *d_bounds, void *stream);
+
+/* ax-2 voxel-grid down-sampling of each frame's emitted rows (Open3D VoxelDownSample semantics:
+ * vmin = min_xyz - vs/2, idx = floor((p - vmin)/vs) on float64 copies, mean of members).
+ *   d_xyz/d_rgb/d_count/d_bounds  outputs of d2pc_emit_enqueue (want_bounds = 1), row stride N
+ *   d_table       scratch of d2pc_voxel_table_bytes() bytes
+ *   d_vox_xyz/rgb float32 [batch, N, 3]; d_vox_idx int32 [batch, N, 3] or NULL;
+ *   d_vox_count   uint32 [batch]; d_vox_error int32 [batch] (1 = index overflow, >= 2^21)     */
+int d2pc_voxel_table_bytes(const D2pcConfig *cfg, size_t *bytes);
+int d2pc_voxel_enqueue(const D2pcConfig *cfg, double voxel_size, const float *d_xyz,
+                       const float *d_rgb, const uint32_t *d_count, const float *d_bounds,
+                       void *d_table, size_t table_bytes, float *d_vox_xyz, float *d_vox_rgb,
+                       int32_t *d_vox_idx, uint32_t *d_vox_count, int32_t *d_vox_error,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2PC_H_ */

@@ -1,0 +1,77 @@
+"""CPU: the product's arithmetic header (csrc/d2pc_math.h, the code the sm_100a kernels run per
+pixel and per frame) compiled for the host and checked against the golden vectors of the
+unmodified reference and against the NumPy oracle."""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import d2pc_oracle as O
+from tests import cases
+from tests.conftest import assert_bits_equal
+from tests.hostmath import harness
+
+
+@pytest.fixture(scope="module")
+def hm():
+    return harness.load()
+
+
+def test_exact_division_by_constant(hm):
+    # reciprocal + two FMA residual steps must equal the IEEE quotient bit for bit
+    for mode in range(4):
+        assert hm.hm_div_check(3_000_000, 100 + mode, mode) == 0
+
+
+def test_resize_matches_oracle(hm):
+    rng = np.random.default_rng(12)
+    for sh, dh in [((19, 27), (24, 32)), ((61, 47), (24, 32)), ((2, 2), (9, 9)), ((518, 686), (480, 640)),
+                   ((37, 53), (1, 1)), ((5, 9), (40, 3))]:
+        d = (rng.random(sh) * 20).astype(np.float32)
+        d.ravel()[rng.choice(d.size, max(1, d.size // 50), replace=False)] = np.inf
+        d.ravel()[rng.choice(d.size, max(1, d.size // 50), replace=False)] = np.nan
+        out = np.empty(dh, np.float32)
+        hm.hm_resize(d.ctypes.data, sh[0], sh[1], out.ctypes.data, dh[0], dh[1])
+        assert_bits_equal(out, O.resize_bilinear(d, dh[0], dh[1]), f"resize {sh}->{dh}")
+
+
+def test_small_goldens_bit_exact(hm, small_golden):
+    for name in small_golden.names:
+        img, dep, kw, pts, cols = small_golden.case(name)
+        if dep.shape[:2] != img.shape[:2] and min(dep.shape[:2]) < 2:
+            continue
+        p, c = harness.run_stage(hm, img, dep, **kw)
+        assert_bits_equal(p, pts, f"{name} points")
+        assert_bits_equal(c, cols, f"{name} colors")
+
+
+@pytest.mark.parametrize("name", ["c1_480p_high", "c1_480p_low_noinv", "c2_1080p_dav2", "c2_1080p_scene_nonfinite"])
+def test_large_goldens_sha(hm, large_golden, name):
+    g = large_golden["cases"][name]
+    img, dep, kw = cases.build_case(cases.LARGE_CASES[name])
+    p, c = harness.run_stage(hm, img, dep, **kw)
+    assert hashlib.sha256(p.tobytes()).hexdigest() == g["points_sha256"]
+    assert hashlib.sha256(c.tobytes()).hexdigest() == g["colors_sha256"]
+
+
+def test_random_against_oracle(hm):
+    rng = np.random.default_rng(21)
+    for t in range(30):
+        H, W = int(rng.integers(1, 40)), int(rng.integers(1, 50))
+        h, w = (H, W) if rng.random() < 0.3 else (int(rng.integers(2, 60)), int(rng.integers(2, 60)))
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        dep = (rng.standard_normal((h, w)) * rng.choice([1.0, 100.0])).astype(np.float32)
+        if t % 3 == 0:
+            k = int(rng.integers(1, h * w // 2 + 2))
+            dep.ravel()[rng.choice(h * w, k, replace=False)] = rng.choice(np.array([np.nan, np.inf, -np.inf], np.float32), k)
+        if t % 7 == 0:
+            dep = np.round(dep)
+        kw = dict(density=str(rng.choice(["low", "medium", "high"])), invert=bool(rng.random() < 0.5),
+                  depth_scale=float(rng.choice([10.0, 1.0, -3.0])))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            po, co = O.depth_to_point_cloud(img, dep, **kw)
+        p, c = harness.run_stage(hm, img, dep, **kw)
+        assert_bits_equal(p, po, f"case {t} {kw}")
+        assert_bits_equal(c, co, f"case {t}")

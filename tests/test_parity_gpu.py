@@ -1,0 +1,231 @@
+"""GPU (-m gpu): the CUDA path, called through the public API / C ABI, against the oracle and the
+golden vectors of the unmodified reference.  Bit-exact for xyz, rgb, masks and voxel indices;
+voxel means within 1e-5 relative (float64 atomics are order-dependent)."""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import d2pc_oracle as O
+from tests import cases
+from tests.conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import image_to_pointcloud_b200 as mod
+    mod.load_library()
+    return mod
+
+
+def _oracle(img, dep, **kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return O.depth_to_point_cloud(img, dep, **kw)
+
+
+def test_small_goldens_bit_exact(m, small_golden):
+    n_run = 0
+    for name in small_golden.names:
+        img, dep, kw, pts, cols = small_golden.case(name)
+        p, c = m.depth_to_point_cloud(img, dep, **kw)
+        assert isinstance(p, np.ndarray) and p.dtype == np.float32 and p.flags["C_CONTIGUOUS"]
+        assert_bits_equal(p, pts, f"{name} points")
+        assert_bits_equal(c, cols, f"{name} colors")
+        n_run += 1
+    assert n_run >= 25
+
+
+@pytest.mark.parametrize("name", list(cases.LARGE_CASES))
+def test_large_goldens_sha(m, large_golden, name):
+    g = large_golden["cases"][name]
+    img, dep, kw = cases.build_case(cases.LARGE_CASES[name])
+    p, c = m.depth_to_point_cloud(img, dep, **kw)
+    assert len(p) == g["n_points"]
+    s = g["sample_stride"]
+    assert p[::s].tobytes().hex() == g["points_sample_hex"], "sampled rows differ from the reference"
+    assert hashlib.sha256(p.tobytes()).hexdigest() == g["points_sha256"]
+    assert hashlib.sha256(c.tobytes()).hexdigest() == g["colors_sha256"]
+
+
+def _engine_run(m, imgs, deps, **kw):
+    import torch
+    force = kw.pop("force_fallback", False)
+    B = len(imgs)
+    H, W = imgs[0].shape[:2]
+    h, w = deps[0].shape[:2]
+    eng = m.FrameEngine(H, W, h, w, batch=B, img_c=3)
+    cfg = eng.make_config(force_fallback=force, **kw)
+    d = torch.from_numpy(np.stack(deps)).cuda()
+    i = torch.from_numpy(np.stack(imgs)).cuda()
+    res = eng.process(cfg, d, i)
+    return eng, cfg, res
+
+
+def test_fallback_path_equals_fast_path_and_oracle(m):
+    """The exact radix-select fallback and the sampled fast path are independent selections:
+    both must give the oracle's percentiles and points."""
+    rng = np.random.default_rng(31)
+    imgs = [rng.integers(0, 256, (120, 200, 3), dtype=np.uint8) for _ in range(4)]
+    deps = [(rng.random((120, 200)) * 20).astype(np.float32),
+            np.round(rng.random((120, 200)) * 20).astype(np.float32),
+            (rng.standard_normal((120, 200)) * 50).astype(np.float32),
+            np.exp(rng.standard_normal((120, 200)) * 3).astype(np.float32)]
+    outs = {}
+    for force in (False, True):
+        eng, cfg, res = _engine_run(m, imgs, deps, density="high", force_fallback=force)
+        prm = eng.frame_params(cfg)
+        outs[force] = (res.xyz.cpu().numpy(), res.rgb.cpu().numpy(), prm)
+        for b in range(4):
+            po, co, info = O.depth_to_point_cloud(imgs[b], deps[b], density="high", return_info=True)
+            assert prm[b]["status"] == 1
+            assert np.float64(prm[b]["p2"]).tobytes() == np.float64(info["p2"]).tobytes(), (force, b)
+            assert np.float64(prm[b]["p98"]).tobytes() == np.float64(info["p98"]).tobytes(), (force, b)
+            assert_bits_equal(outs[force][0][b], po, f"force={force} frame {b}")
+            assert_bits_equal(outs[force][1][b], co, f"force={force} frame {b}")
+    assert outs[False][2][0]["reserved"][0] == 0, "fast path should not have failed on uniform data"
+
+
+def test_batch_with_mixed_frames(m):
+    """One batch: clean frame, NaN/inf frame (fallback), constant frame (zeros branch), two-outlier
+    frame (min/max branch), heavy-tie frame.  Each frame must match the oracle on its own."""
+    rng = np.random.default_rng(32)
+    H, W = 96, 160
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(5)]
+    deps = [cases.make_depth(H, W, 1, "uniform"), cases.make_depth(H, W, 2, "nonfinite"),
+            cases.make_depth(H, W, 3, "constant"), cases.make_depth(H, W, 4, "two_outliers"),
+            cases.make_depth(H, W, 5, "ties")]
+    for kw in (dict(density="high"), dict(density="medium", invert=False, depth_scale=3.5)):
+        eng, cfg, res = _engine_run(m, imgs, deps, **kw)
+        prm = eng.frame_params(cfg)
+        assert [p["branch"] for p in prm] == [0, 0, 2, 1, 0]
+        assert prm[1]["n_nonfinite"] > 0
+        for b in range(5):
+            po, co = _oracle(imgs[b], deps[b], **kw)
+            assert int(res.count[b]) == len(po)
+            assert_bits_equal(res.xyz[b].cpu().numpy(), po, f"{kw} frame {b}")
+            assert_bits_equal(res.rgb[b].cpu().numpy(), co, f"{kw} frame {b}")
+
+
+def test_resized_batch_all_strides(m):
+    rng = np.random.default_rng(33)
+    H, W, h, w = 121, 161, 77, 91
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(3)]
+    deps = [(rng.random((h, w)) * 20).astype(np.float32) for _ in range(3)]
+    deps[1][5, 5] = np.nan
+    deps[1][0, 0] = np.inf  # corner tap: IPP turns it into NaN
+    for dens in ("low", "medium", "high"):
+        eng, cfg, res = _engine_run(m, imgs, deps, density=dens)
+        for b in range(3):
+            po, co = _oracle(imgs[b], deps[b], density=dens)
+            assert_bits_equal(res.xyz[b].cpu().numpy(), po, f"{dens} frame {b}")
+            assert_bits_equal(res.rgb[b].cpu().numpy(), co, f"{dens} frame {b}")
+
+
+def test_percentile_selection_on_hard_distributions(m):
+    """Exact order statistics for sizes above the sampling threshold, incl. ReLU-style zeros."""
+    rng = np.random.default_rng(34)
+    H, W = 360, 640
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    variants = {
+        "uniform": (rng.random((H, W)) * 20).astype(np.float32),
+        "relu_zeros_30pct": np.maximum(rng.standard_normal((H, W)) - 0.5, 0).astype(np.float32),
+        "narrow": (10 + rng.random((H, W)) * 1e-3).astype(np.float32),
+        "quantised": np.round(rng.random((H, W)) * 50).astype(np.float32),
+        "lognormal": np.exp(rng.standard_normal((H, W)) * 4).astype(np.float32),
+        "negative": (-np.exp(rng.standard_normal((H, W)))).astype(np.float32),
+        "sorted_ramp": np.linspace(0, 1, H * W, dtype=np.float32).reshape(H, W),
+        "periodic": np.tile(np.arange(W, dtype=np.float32) % 27, (H, 1)),
+    }
+    for name, dep in variants.items():
+        eng, cfg, res = _engine_run(m, [img], [dep], density="medium")
+        prm = eng.frame_params(cfg)[0]
+        po, co, info = O.depth_to_point_cloud(img, dep, density="medium", return_info=True)
+        assert np.float64(prm["p2"]).tobytes() == np.float64(info["p2"]).tobytes(), name
+        assert np.float64(prm["p98"]).tobytes() == np.float64(info["p98"]).tobytes(), name
+        assert_bits_equal(res.xyz[0].cpu().numpy(), po, name)
+
+
+def test_range_mask_and_compaction(m):
+    rng = np.random.default_rng(35)
+    for (H, W, h, w) in [(96, 160, 96, 160), (121, 161, 77, 91), (300, 500, 300, 500)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        dep = (rng.random((h, w)) * 20).astype(np.float32)
+        dep[3, 4] = np.nan
+        for dens in ("high", "medium"):
+            for zr in ((0.5, 9.5), (2.0, 2.5), (20.0, 30.0), (0.0, 10.0)):
+                po, co = _oracle(img, dep, density=dens)
+                keep = O.range_mask(po, *zr)
+                p, c = m.depth_to_point_cloud(img, dep, density=dens, z_range=zr)
+                assert len(p) == int(keep.sum()), (H, W, dens, zr)
+                assert_bits_equal(p, po[keep], f"mask {zr} points")   # raster order preserved
+                assert_bits_equal(c, co[keep], f"mask {zr} colors")
+    # drop_nonfinite drops the repaired pixels
+    po, co = _oracle(img, dep, density="high")
+    p, c = m.depth_to_point_cloud(img, dep, density="high", drop_nonfinite=True)
+    fin = np.isfinite(dep).ravel()
+    assert_bits_equal(p, po[fin], "drop_nonfinite")
+
+
+def test_voxel_downsample(m):
+    rng = np.random.default_rng(36)
+    H, W = 240, 320
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    dep = cases.make_depth(H, W, 9, "scene")
+    for vs in (0.05, 0.5, 0.005):
+        for zr in (None, (0.5, 9.5)):
+            po, co = _oracle(img, dep, density="high")
+            if zr is not None:
+                po, co, _ = O.apply_range_mask(po, co, *zr)
+            vp, vc, vidx = O.voxel_downsample(po, co, vs)
+            p, c, idx = m.depth_to_point_cloud(img, dep, density="high", z_range=zr, voxel_size=vs,
+                                               return_voxel_index=True)
+            assert len(p) == len(vp), (vs, zr)
+            key = (idx[:, 0].astype(np.int64) << 42) | (idx[:, 1].astype(np.int64) << 21) | idx[:, 2]
+            order = np.argsort(key)
+            assert np.array_equal(idx[order], vidx), "voxel indices must be bit-exact"
+            np.testing.assert_allclose(p[order], vp, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(c[order], vc, rtol=1e-5, atol=1e-4)
+    with pytest.raises(ValueError):
+        m.depth_to_point_cloud(img, dep, density="high", voxel_size=1e-9)
+
+
+def test_host_pipeline_matches_single_calls(m):
+    rng = np.random.default_rng(37)
+    H, W = 120, 200
+    n = 11
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(n)]
+    deps = [(rng.random((H, W)) * (5 + i)).astype(np.float32) for i in range(n)]
+    deps[4][7, 7] = np.inf
+    outs = m.depth_to_point_cloud_batch(imgs, deps, density="high", chunk=4)
+    assert len(outs) == n
+    for i in range(n):
+        po, co = _oracle(imgs[i], deps[i], density="high")
+        assert_bits_equal(outs[i][0], po, f"frame {i}")
+        assert_bits_equal(outs[i][1], co, f"frame {i}")
+    outs = m.depth_to_point_cloud_batch(imgs[:3], deps[:3], density="medium", z_range=(1.0, 8.0), chunk=8)
+    for i in range(3):
+        po, co = _oracle(imgs[i], deps[i], density="medium")
+        keep = O.range_mask(po, 1.0, 8.0)
+        assert_bits_equal(outs[i][0], po[keep], f"masked frame {i}")
+
+
+def test_4k_full_size_properties_and_oracle(m):
+    """BASELINE config 3 size: full compare against the oracle plus size-independent properties."""
+    img, dep, kw = cases.build_case(cases.LARGE_CASES["c3_4k_dav2"])
+    p, c = m.depth_to_point_cloud(img, dep, **kw)
+    assert p.shape == (2160 * 3840, 3)
+    assert np.array_equal(c, img[:, :, ::-1].reshape(-1, 3).astype(np.float32))  # colour gather exact
+    zmax = p[:, 2].max()
+    assert 0.0 <= p[:, 2].min() and zmax <= 10.0
+    assert p[1080 * 3840 + 1920, 0] == 0.0 and p[1080 * 3840 + 1920, 1] == 0.0  # u=cx, v=cy
+    po, co = _oracle(img, dep, **kw)
+    assert_bits_equal(p, po, "4K points")
+    # idempotence: same input, same bits
+    p2, _ = m.depth_to_point_cloud(img, dep, **kw)
+    assert np.array_equal(p.view(np.uint32), p2.view(np.uint32))
