@@ -15,7 +15,8 @@ namespace d2pc {
 // ------------------------------------------------------------------------------------------
 constexpr int kSampleSize = 8192;      // level-1 sample per frame (stratified), power of two
 constexpr int kSample2Size = 4096;     // level-2 sample over a bracket's candidates
-constexpr int kSortCap = 16384;        // keys one CTA sorts in shared memory (64 KB)
+constexpr int kSortCap = 16384;        // frames with at most this many pixels skip sampling
+constexpr int kSelCap = 49152;         // keys one select CTA can hold in shared memory (192 KB)
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 16;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // 4096 pixels per CTA
@@ -203,6 +204,65 @@ __device__ __forceinline__ void block_bitonic_sort(uint32_t *s, uint32_t n) {
       __syncthreads();
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact order statistics without sorting: bisection on the key bits.  For every target t,
+// out[t] = the rank[t]-th smallest key (0-based) among all keys the CTA holds.  32 rounds, each
+// a counting pass (key < trial) + one barrier; T targets share the passes.  s_cnt: 3*T words of
+// shared memory, zeroed by the caller (followed by a barrier).  Every thread gets the results.
+// ------------------------------------------------------------------------------------------
+template <int T, typename CountFn>
+__device__ __forceinline__ void block_bisect(const uint32_t (&rank)[T], uint32_t (&out)[T], uint32_t *s_cnt,
+                                             CountFn count_below) {
+  uint32_t K[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) K[t] = 0u;
+  int buf = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    uint32_t trial[T], c[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { trial[t] = K[t] | (1u << bit); c[t] = 0u; }
+    count_below(trial, c);  // c[t] += number of this thread's keys < trial[t]
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      c[t] = warp_sum(c[t]);
+      if ((threadIdx.x & 31) == 0 && c[t]) atomicAdd(&s_cnt[buf * T + t], c[t]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (s_cnt[buf * T + t] <= rank[t]) K[t] = trial[t];
+    // the buffer used two rounds from now was last read one round ago: safe to clear here
+    const int clr = (buf + 2) % 3;
+    if (threadIdx.x < T) s_cnt[clr * T + threadIdx.x] = 0u;
+    buf = (buf + 1) % 3;
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) out[t] = K[t];
+}
+
+template <int E, int T>
+__device__ __forceinline__ void block_select_regs(const uint32_t (&k)[E], const uint32_t (&rank)[T],
+                                                  uint32_t (&out)[T], uint32_t *s_cnt) {
+  block_bisect<T>(rank, out, s_cnt, [&](const uint32_t (&trial)[T], uint32_t (&c)[T]) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int t = 0; t < T; ++t) c[t] += (k[e] < trial[t]) ? 1u : 0u;
+  });
+}
+
+template <int T>
+__device__ __forceinline__ void block_select_smem(const uint32_t *sk, uint32_t n, const uint32_t (&rank)[T],
+                                                  uint32_t (&out)[T], uint32_t *s_cnt) {
+  block_bisect<T>(rank, out, s_cnt, [&](const uint32_t (&trial)[T], uint32_t (&c)[T]) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = sk[i];
+#pragma unroll
+      for (int t = 0; t < T; ++t) c[t] += (key < trial[t]) ? 1u : 0u;
+    }
+  });
 }
 
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32

@@ -12,6 +12,8 @@
 //     compacted rows of a tile go to `prefix` rows found by a decoupled look-back over the
 //     frame's tiles, so the output keeps raster order (the reference's preview stride
 //     points[::stride], app.py:498-500, depends on it).
+#include <stdlib.h>
+
 #include "d2pc_device.cuh"
 
 namespace d2pc {
@@ -67,65 +69,133 @@ __device__ __forceinline__ void copy_out(const float *s, uint32_t s_off, uint32_
 }
 
 // ------------------------------------------------------------------------------------------
-// fast path: step 1, native depth, 3-channel image, P % 4 == 0, no mask
+// fast path: step 1, native depth, 3-channel image, W % 4 == 0, no mask
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEmitThreads) emit_fast_kernel(KParams kp, EmitArgs ea) {
-  __shared__ __align__(16) float s_xyz[kEmitTile * 3];
-  __shared__ __align__(16) float s_rgb[kEmitTile * 3];
-  __shared__ uint32_t s_b[6][kEmitThreads / 32];
-  const int b = blockIdx.y, tid = threadIdx.x;
-  FrameState *fs = kp.state + b;
-  if (fs->status != D2PC_FRAME_READY) return;
-  const NormParams np_ = fs->norm;
+// u8 -> f32 without the conversion pipe: byte k of w into the mantissa of 2^23, minus 2^23.
+__device__ __forceinline__ float byte_to_float(uint32_t w, uint32_t selector) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, selector)) - 8388608.0f;
+}
+#define D2PC_B0 0x7440u
+#define D2PC_B1 0x7441u
+#define D2PC_B2 0x7442u
+#define D2PC_B3 0x7443u
+
+// Persistent CTAs (grid = resident CTAs), round-robin over the (frame, tile) list.  Each thread
+// owns 4 consecutive pixels of a tile; the 28 bytes it needs for its NEXT tile are requested
+// before it starts computing the current one (register double buffering), so HBM latency is
+// overlapped with the FP64 chain.  Staging smem is double buffered: one barrier per tile.
+struct FastArgs {
+  uint32_t tiles_per_frame, total_tiles;
+  unsigned long long magic_w;  // ceil(2^40 / W): p / W == (p * magic_w) >> 40 for p * W < 2^40
+  int32_t pc_simple;
+};
+
+struct FastRegs {
+  float4 d4;
+  uint32_t c0, c1, c2;
+};
+
+__device__ __forceinline__ void fast_prefetch(const KParams &kp, const EmitArgs &ea, const FastArgs &fa,
+                                              uint32_t t, int tid, FastRegs &r) {
+  const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
+  const uint32_t p0 = tile * (uint32_t)kEmitTile + 4u * (uint32_t)tid;
+  if (p0 < kp.g.P) {
+    r.d4 = ldg_stream_f4(kp.depth + (size_t)b * kp.g.P + p0);
+    const uint8_t *cp = ea.bgr + ((size_t)b * kp.g.P + p0) * 3;
+    r.c0 = ldg_stream_u32(cp); r.c1 = ldg_stream_u32(cp + 4); r.c2 = ldg_stream_u32(cp + 8);
+  }
+}
+
+// PREFETCH: persistent round-robin loop with register double buffering; otherwise one tile per CTA.
+template <bool PREFETCH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KParams kp, EmitArgs ea, FastArgs fa) {
+  extern __shared__ __align__(16) float s_stage[];  // [2 buffers][xyz 3072 | rgb 3072]
+  const int tid = threadIdx.x;
   const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
-  const uint32_t tile_base = blockIdx.x * (uint32_t)kEmitTile;
-  const uint32_t p0 = tile_base + 4u * (uint32_t)tid;
-  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
-  if (p0 < P) {
-    const float4 d4 = ldg_stream_f4(kp.depth + (size_t)b * P + p0);
-    const uint8_t *cp = ea.bgr + ((size_t)b * P + p0) * 3;
-    const uint32_t c0 = ldg_stream_u32(cp), c1 = ldg_stream_u32(cp + 4), c2 = ldg_stream_u32(cp + 8);
-    uint32_t v = p0 / W, u = p0 - v * W;
-    const float raw[4] = {d4.x, d4.y, d4.z, d4.w};
-    float o[12];
+  uint32_t t = blockIdx.x;
+  if (t >= fa.total_tiles) return;
+  FastRegs cur, nxt;
+  fast_prefetch(kp, ea, fa, t, tid, cur);
+  int buf = 0;
+  while (t < fa.total_tiles) {
+    const uint32_t tn = PREFETCH ? t + gridDim.x : fa.total_tiles;
+    if (PREFETCH && tn < fa.total_tiles) fast_prefetch(kp, ea, fa, tn, tid, nxt);
+    const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
+    const FrameState *fs = kp.state + b;
+    const uint32_t tile_base = tile * (uint32_t)kEmitTile;
+    const uint32_t p0 = tile_base + 4u * (uint32_t)tid;
+    float *s_xyz = s_stage + buf * (2 * kEmitTile * 3);
+    float *s_rgb = s_xyz + kEmitTile * 3;
+    const bool ready = fs->status == D2PC_FRAME_READY;  // uniform per CTA
+    if (ready && p0 < P) {
+      const NormParams np_ = fs->norm;
+      const uint32_t v = (uint32_t)(((unsigned long long)p0 * fa.magic_w) >> 40), u = p0 - v * W;
+      const float raw[4] = {cur.d4.x, cur.d4.y, cur.d4.z, cur.d4.w};
+      float o[12];
+      if (np_.simple && fa.pc_simple) {  // uniform per frame
+        const double ux0 = (double)(int32_t)u - ea.pc.cx;
+        const double vy = (double)(int32_t)v - ea.pc.cy;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (u >= W) { u -= W; v += 1; }
-      const double n = normalised_depth(raw[k], np_, ea.pc.invert);
-      back_project(n, (int32_t)u, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
-      u += 1;
-    }
-    if (ea.want_bounds) {
+        for (int k = 0; k < 4; ++k)
+          simple_point(raw[k], ux0 + (double)k, vy, np_, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          uint32_t key = float_to_key(o[3 * k + c]);
-          mn[c] = min(mn[c], key); mx[c] = max(mx[c], key);
+        for (int k = 0; k < 4; ++k) {
+          const double n = normalised_depth(raw[k], np_, ea.pc.invert);
+          back_project(n, (int32_t)u + k, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
         }
+      }
+      float *sx = s_xyz + 12 * tid;
+      stage_f4(sx, o[0], o[1], o[2], o[3]);
+      stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
+      stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
+      // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
+      const uint32_t c0 = cur.c0, c1 = cur.c1, c2 = cur.c2;
+      float *sr = s_rgb + 12 * tid;
+      stage_f4(sr, byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
+               byte_to_float(c1, D2PC_B1));
+      stage_f4(sr + 4, byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3), byte_to_float(c2, D2PC_B0),
+               byte_to_float(c1, D2PC_B3));
+      stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
+               byte_to_float(c2, D2PC_B1));
     }
-    float *sx = s_xyz + 12 * tid;
-    stage_f4(sx, o[0], o[1], o[2], o[3]);
-    stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
-    stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
-    // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
-    float *sr = s_rgb + 12 * tid;
-    stage_f4(sr, (float)((c0 >> 16) & 255u), (float)((c0 >> 8) & 255u), (float)(c0 & 255u),
-             (float)((c1 >> 8) & 255u));
-    stage_f4(sr + 4, (float)(c1 & 255u), (float)(c0 >> 24), (float)(c2 & 255u), (float)(c1 >> 24));
-    stage_f4(sr + 8, (float)((c1 >> 16) & 255u), (float)(c2 >> 24), (float)((c2 >> 16) & 255u),
-             (float)((c2 >> 8) & 255u));
+    __syncthreads();
+    if (ready) {
+      const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
+      const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
+      const uint32_t nvec = rows * 3u / 4u;  // rows % 4 == 0 here
+      for (uint32_t i = tid; i < nvec; i += kEmitThreads) {
+        stg_stream_f4(ea.xyz + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_xyz + 4 * i));
+        stg_stream_f4(ea.rgb + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_rgb + 4 * i));
+      }
+      if (tile == 0 && tid == 0) ea.count[b] = kp.g.N;
+    }
+    buf ^= 1;
+    t = tn;
+    if (PREFETCH) cur = nxt;
   }
-  __syncthreads();
-  const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
-  const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
-  const uint32_t nvec = rows * 3u / 4u;  // rows % 4 == 0 here
-  for (uint32_t i = tid; i < nvec; i += kEmitThreads) {
-    stg_stream_f4(ea.xyz + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_xyz + 4 * i));
-    stg_stream_f4(ea.rgb + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_rgb + 4 * i));
+}
+
+template <bool PREFETCH, int MIN_BLOCKS>
+static int launch_emit_fast(const KParams &kp, const EmitArgs &ea, const FastArgs &fa, cudaStream_t st) {
+  const size_t smem = (PREFETCH ? 2 : 1) * 2 * (size_t)kEmitTile * 3 * sizeof(float);  // 48 / 24 KB
+  cudaError_t e = cudaFuncSetAttribute(emit_fast_kernel<PREFETCH, MIN_BLOCKS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return record_cuda_error(e);
+  uint32_t ctas = fa.total_tiles;
+  if (PREFETCH) {
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_fast_kernel<PREFETCH, MIN_BLOCKS>,
+                                                      kEmitThreads, smem);
+    if (e != cudaSuccess) return record_cuda_error(e);
+    if (per_sm < 1) per_sm = 1;
+    ctas = (uint32_t)sms * (uint32_t)per_sm;  // persistent: exactly one resident wave
+    if (ctas > fa.total_tiles) ctas = fa.total_tiles;
   }
-  if (blockIdx.x == 0 && tid == 0) ea.count[b] = kp.g.N;
-  if (ea.want_bounds) reduce_bounds(fs, mn, mx, s_b);
+  emit_fast_kernel<PREFETCH, MIN_BLOCKS><<<ctas, kEmitThreads, smem, st>>>(kp, ea, fa);
+  return D2PC_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -158,7 +228,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
   __shared__ __align__(16) float s_xyz[kEmitTile * 3 + 4];
   __shared__ __align__(16) float s_rgb[kEmitTile * 3 + 4];
   __shared__ uint32_t s_warp[kEmitThreads / 32];
-  __shared__ uint32_t s_prefix, s_total;
+  __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_b[6][kEmitThreads / 32];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -317,10 +387,31 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     D2PC_CHECK_LAUNCH();
   }
   dim3 grid(kp.emit_tiles, cfg->batch);
-  const bool fast = !mask && kp.g.native && cfg->step == 1 && cfg->img_c == 3 && (kp.g.P & 3u) == 0u &&
-                    (((uintptr_t)d_depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u);
+  const bool fast = !mask && !cfg->want_bounds && kp.g.native && cfg->step == 1 && cfg->img_c == 3 &&
+                    (cfg->img_w & 3) == 0 && (((uintptr_t)d_depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) &&
+                    ((unsigned long long)kp.g.P * (unsigned long long)cfg->img_w < (1ull << 40));
   if (fast) {
-    emit_fast_kernel<<<grid, kEmitThreads, 0, st>>>(kp, ea);
+    FastArgs fa;
+    fa.tiles_per_frame = kp.emit_tiles;
+    fa.total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
+    fa.magic_w = ((1ull << 40) + (unsigned long long)cfg->img_w - 1ull) / (unsigned long long)cfg->img_w;
+    fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
+    static int variant = -1;  // tuning knob (D2PC_EMIT_VARIANT), default chosen from measurements
+    if (variant < 0) {
+      const char *v = getenv("D2PC_EMIT_VARIANT");
+      variant = v ? atoi(v) : 5;
+    }
+    int rcl;
+    switch (variant) {
+      case 0: rcl = launch_emit_fast<true, 3>(kp, ea, fa, st); break;
+      case 1: rcl = launch_emit_fast<true, 4>(kp, ea, fa, st); break;
+      case 3: rcl = launch_emit_fast<false, 5>(kp, ea, fa, st); break;
+      case 4: rcl = launch_emit_fast<false, 3>(kp, ea, fa, st); break;
+      case 6: rcl = launch_emit_fast<false, 8>(kp, ea, fa, st); break;
+      case 2: rcl = launch_emit_fast<false, 4>(kp, ea, fa, st); break;
+      default: rcl = launch_emit_fast<false, 6>(kp, ea, fa, st); break;
+    }
+    if (rcl) return rcl;
   } else if (kp.g.native) {
     if (mask) emit_generic_kernel<true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);
     else emit_generic_kernel<true, false><<<grid, kEmitThreads, 0, st>>>(kp, ea);

@@ -170,6 +170,10 @@ struct NormParams {  // what the emit kernel needs, one per frame
   float lo32, hi32, den32, median;
   int32_t branch;
   int32_t has_nonfinite;
+  // guard-free fast path (see finish_norm): valid iff simple != 0
+  float clip_lo_f, clip_hi_f;  // for float32 d:  d < p2 <=> d < clip_lo_f ;  d > p98 <=> d > clip_hi_f
+  int32_t simple;
+  int32_t pad_;
 };
 
 // p2/p98: interpolated percentiles (float64); vmin/vmax: min/max of the repaired float32 map.
@@ -214,9 +218,36 @@ D2PC_HD double div_by_const(double a, double b, double y) {
   double q2 = fma(r1, y, q1);
   // guard: anything exotic (inf/NaN operands, overflow, deep underflow) -> plain division
   double aq = fabs(q2);
-  if (!(aq < 1e300) || (aq < 1e-290 && a != 0.0)) return a / b;
+  if (!(aq < 1e300) || aq < 1e-290) return a / b;  // also a == +-0: IEEE signed zero
   return q2;
 }
+
+// Same quotient without the guard, for callers that have established (per frame / per call) that
+// a is finite, |a| is 0 or within [1e-200, 1e200], and b, y are finite and normal: then no
+// intermediate over/underflows and the two-step correction is exact.  The sign is patched from
+// the operands so that a == -0.0 (or +0.0 with b < 0) yields the IEEE signed zero.
+D2PC_HD double div_by_const_fast(double a, double b, double y) {
+  double q0 = a * y;
+  double r0 = fma(-b, q0, a);
+  double q1 = fma(r0, y, q0);
+  double r1 = fma(-b, q1, a);
+  return fma(r1, y, q1);
+}
+D2PC_HD double patch_quotient_sign(double q, double a, double b) {
+#if defined(__CUDA_ARCH__)
+  int hi = __double2hiint(q), lo = __double2loint(q);
+  int s = (__double2hiint(a) ^ __double2hiint(b)) & 0x80000000;
+  return __hiloint2double((hi & 0x7FFFFFFF) | s, lo);
+#else
+  uint64_t uq, ua, ub;
+  memcpy(&uq, &q, 8); memcpy(&ua, &a, 8); memcpy(&ub, &b, 8);
+  uq = (uq & 0x7FFFFFFFFFFFFFFFull) | ((ua ^ ub) & 0x8000000000000000ull);
+  memcpy(&q, &uq, 8);
+  return q;
+#endif
+}
+
+D2PC_HD bool finite_mid_range(double x) { double a = fabs(x); return a == 0.0 || (a > 1e-100 && a < 1e100); }
 
 // ---------------------------------------------------------------------------------------------
 // a2 + a4 + a5 + a9  one pixel: raw (resized) depth -> xyz (app.py:193-206, 231-237)
@@ -262,6 +293,51 @@ D2PC_HD void back_project(double n, int32_t u, int32_t v, const PixelConsts &pc,
   double ay = ((double)v - pc.cy) * zz;
   *x = (float)div_by_const(ax, pc.f, pc.inv_f);  // ... / f   (rounded), then np.float32
   *y = (float)div_by_const(ay, pc.f, pc.inv_f);
+  *z = (float)zd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "simple frame" fast path: percentile branch, finite mid-range parameters, no non-finite pixel,
+// and (per call) depth_scale > 0, f > 0.  Straight-line code without guards or sign patches;
+// bit-identical to normalised_depth()/back_project() on such frames:
+//   * every quotient is 0 or lies in [1e-200, 1e200], so div_by_const_fast is exact;
+//   * numerators are >= +0 or have a non-zero magnitude, so no signed-zero case differs, except
+//     a = c - p2 = -0.0 (d == -0.0 with p2 == +0.0), which is patched.
+// Call after has_nonfinite has been set.
+// ---------------------------------------------------------------------------------------------
+D2PC_HD void finish_norm(NormParams *o) {
+  o->simple = 0;
+  o->clip_lo_f = o->clip_hi_f = 0.0f;
+  o->pad_ = 0;
+  if (o->branch != D2PC_BRANCH_PCT || o->has_nonfinite) return;
+  if (!finite_mid_range(o->p2) || !finite_mid_range(o->p98) || !finite_mid_range(o->den) || o->den == 0.0) return;
+  float lo = (float)o->p2;   // round to nearest, then move to the float32 ceiling of p2
+  if ((double)lo < o->p2) lo = bits_f32(lo >= 0.0f ? f32_bits(lo) + 1u : f32_bits(lo) - 1u);
+  float hi = (float)o->p98;  // float32 floor of p98
+  if ((double)hi > o->p98) hi = bits_f32(hi > 0.0f ? f32_bits(hi) - 1u : f32_bits(hi) + 1u);
+  if (!is_finite_f32(lo) || !is_finite_f32(hi)) return;
+  o->clip_lo_f = lo;
+  o->clip_hi_f = hi;
+  o->simple = 1;
+}
+D2PC_HD bool consts_simple(const PixelConsts &pc) {
+  return pc.scale > 1e-100 && pc.scale < 1e100 && pc.f > 1e-100 && pc.f < 1e100 && fabs(pc.cx) < 1e100 &&
+         fabs(pc.cy) < 1e100;
+}
+
+// ux = (double)u - cx, vy = (double)v - cy (both exact)
+D2PC_HD void simple_point(float d, double ux, double vy, const NormParams &sn, const PixelConsts &pc,
+                          float *x, float *y, float *z) {
+  double c = (double)d;
+  c = (d < sn.clip_lo_f) ? sn.p2 : c;
+  c = (d > sn.clip_hi_f) ? sn.p98 : c;
+  double a = c - sn.p2;  // >= 0, but -0.0 when d == -0.0 and p2 == +0.0: keep the IEEE sign
+  double n = patch_quotient_sign(div_by_const_fast(a, sn.den, sn.inv_den), a, sn.den);
+  if (pc.invert) n = 1.0 - n;
+  double zd = n * pc.scale;
+  double zz = (zd != 0.0) ? zd : 1e-6;
+  *x = (float)div_by_const_fast(ux * zz, pc.f, pc.inv_f);
+  *y = (float)div_by_const_fast(vy * zz, pc.f, pc.inv_f);
   *z = (float)zd;
 }
 

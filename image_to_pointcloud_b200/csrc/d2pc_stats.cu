@@ -3,14 +3,16 @@
 // non-finite repair (np.nanmedian) and the frame's normalisation parameters.
 //
 // Fast path (3 launches per batch, depth map read from HBM exactly once):
-//   sample_kernel  1 CTA/frame   stratified sample -> bitonic sort in smem -> key brackets
-//                                [L, U] that contain the wanted ranks with ~6 sigma margin
+//   sample_kernel  1 CTA/frame   stratified sample (registers) -> exact sample order statistics
+//                                by bisection on the key bits -> key brackets [L, U] that
+//                                contain the wanted ranks with ~6 sigma margin
 //   scan_kernel    streaming     per key: count below / equal-to-bound, append the few keys
 //                                strictly inside a bracket (about 2% each) to a candidate list,
 //                                min/max, non-finite counts.  Pure compares, no histogram:
 //                                the only atomics are per CTA.
-//   select_kernel  2 CTA/frame   exact rank selection inside the candidate list (direct smem
-//                                sort, or a second sample/bracket level for long lists), then
+//   select_kernel  2 CTA/frame   exact rank selection inside the candidate list (bisection over
+//                                the keys in smem; a second sample/bracket level first when
+//                                the list does not fit), then
 //                                the last CTA of a frame evaluates NumPy's _lerp in float64
 //                                and writes the parameter block.
 // Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, candidate
@@ -30,8 +32,8 @@ __device__ __forceinline__ int32_t bracket_margin(double q, int S) {
 // ------------------------------------------------------------------------------------------
 template <bool NATIVE>
 __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
-  extern __shared__ uint32_t skeys[];
   __shared__ uint32_t s_bad;
+  __shared__ uint32_t s_cnt[3 * 4];
   const int b = blockIdx.x;
   FrameState *fs = kp.state + b;
   const float *frame = kp.depth + (size_t)b * kp.g.D;
@@ -50,7 +52,9 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     fs->fb_active = 0; fs->fb_any_nan = 0;
     fs->norm.has_nonfinite = 0;
     fs->norm.median = 0.0f;
+    fs->norm.simple = 0;
   }
+  if (tid < 12) s_cnt[tid] = 0;
   if (n <= (uint32_t)kSortCap) {  // small frame: every finite key is a candidate
     if (tid == 0) {
       fs->brL[0] = fs->brL[1] = 0u;
@@ -59,30 +63,43 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     }
     return;
   }
-  __syncthreads();
+  // stratified sample, kSampleSize / blockDim keys per thread, kept in registers
+  constexpr int E = kSampleSize / kSelThreads;
   const uint32_t S = kSampleSize;
-  for (uint32_t j = tid; j < S; j += blockDim.x) {
+  uint32_t k[E];
+  bool bad = false;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const uint32_t j = (uint32_t)e * kSelThreads + (uint32_t)tid;
     uint32_t start = (uint32_t)(((unsigned long long)j * n) / S);
     uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * n) / S);
-    uint32_t width = end - start;
-    uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)b * 0x85EBCA6Bu + 12345u) % width;
+    uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)b * 0x85EBCA6Bu + 12345u) % (end - start);
     float v = depth_at<NATIVE>(frame, kp.g, idx);
-    uint32_t key = 0xFFFFFFFFu;
-    if (is_finite_f32(v)) key = float_to_key(v); else atomicOr(&s_bad, 1u);
-    skeys[j] = key;
+    k[e] = 0xFFFFFFFFu;
+    if (is_finite_f32(v)) k[e] = float_to_key(v); else bad = true;
   }
+  if (bad) atomicOr(&s_bad, 1u);
   __syncthreads();
-  block_bitonic_sort(skeys, S);
-  if (tid < 2) {
-    const int br = tid;
+  // sample ranks that bracket the wanted order statistics with a ~6 sigma margin
+  uint32_t rank[4], out[4];
+  bool open_lo[2], open_hi[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
     const double q = br ? D2PC_Q98 : D2PC_Q02;
     RankPair rp = percentile_ranks(n, q);
     long long i_lo = (long long)(((unsigned long long)rp.lo * S) / n);
     long long i_hi = (long long)(((unsigned long long)rp.hi * S) / n) + 1;
     int32_t m = bracket_margin(q, (int)S);
     long long iL = i_lo - m, iU = i_hi + m;
-    fs->brL[br] = iL < 0 ? 0u : skeys[iL];
-    fs->brU[br] = iU >= (long long)S ? 0xFFFFFFFFu : skeys[iU];
+    open_lo[br] = iL < 0;
+    open_hi[br] = iU >= (long long)S;
+    rank[2 * br + 0] = open_lo[br] ? 0u : (uint32_t)iL;
+    rank[2 * br + 1] = open_hi[br] ? S - 1 : (uint32_t)iU;
+  }
+  block_select_regs<E, 4>(k, rank, out, s_cnt);
+  if (tid < 2) {
+    fs->brL[tid] = open_lo[tid] ? 0u : out[2 * tid + 0];
+    fs->brU[tid] = open_hi[tid] ? 0xFFFFFFFFu : out[2 * tid + 1];
   }
   if (tid == 0) fs->sample_ok = s_bad ? 0u : 1u;
 }
@@ -90,52 +107,73 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
 // ------------------------------------------------------------------------------------------
 // scan_kernel
 // ------------------------------------------------------------------------------------------
-struct ScanAcc {
-  uint32_t below[2], eqL[2], eqU[2], nf, nan, mn, mx;
+// One streaming pass, ~10 instructions per pixel on the common path: float compares against the
+// bracket bounds (as floats; -0.0 == +0.0 here and in the rare path, consistently), per-thread
+// "below" counters, and a rare path (about 4% of pixels: inside a bracket, or non-finite) that
+// appends the key to the CTA's staging list or bumps an equal-to-bound / non-finite counter.
+// min/max are not tracked: a frame whose percentiles collapse (p98 <= p2) goes to the exact
+// fallback, which computes them.
+struct ScanShared {
+  uint32_t cand[2][kScanTile];
+  uint32_t cnt[2], eqL[2], eqU[2], nf, nan;
+  uint32_t base[2];
+  uint32_t red[2][kScanThreads / 32];
 };
 
-__device__ __forceinline__ void scan_value(float v, const uint32_t L[2], const uint32_t U[2],
-                                           ScanAcc &a, uint32_t (*s_cand)[kScanTile],
-                                           uint32_t *s_cnt) {
-  uint32_t bits = f32_bits(v);
-  if ((bits & 0x7F800000u) == 0x7F800000u) {
-    a.nf++;
-    if (bits & 0x007FFFFFu) a.nan++;
+__device__ __forceinline__ void scan_rare(float v, const float Lf[2], const float Uf[2], ScanShared &sh) {
+  if (!(fabsf(v) < __int_as_float(0x7F800000))) {
+    atomicAdd(&sh.nf, 1u);
+    if (v != v) atomicAdd(&sh.nan, 1u);
     return;
   }
-  uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
-  a.mn = min(a.mn, key);
-  a.mx = max(a.mx, key);
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
-    if (key < L[br]) a.below[br]++;
-    else if (key == L[br]) a.eqL[br]++;
-    else if (key < U[br]) {
-      uint32_t pos = atomicAdd(&s_cnt[br], 1u);
-      s_cand[br][pos] = key;
-    } else if (key == U[br]) a.eqU[br]++;
+    if (v >= Lf[br] && v <= Uf[br]) {
+      if (v == Lf[br]) atomicAdd(&sh.eqL[br], 1u);
+      else if (v < Uf[br]) {
+        uint32_t pos = atomicAdd(&sh.cnt[br], 1u);
+        sh.cand[br][pos] = float_to_key(v);
+      } else atomicAdd(&sh.eqU[br], 1u);
+    }
   }
+}
+
+// Common path: count "below", and only FLAG the element (bit `bit` of `rare`) when it is inside a
+// bracket or non-finite.  Flagged elements (about 4%) are handled after the streaming loop, so
+// the hot loop has no divergent branch.
+__device__ __forceinline__ void scan_value(float v, const float Lf[2], const float Uf[2], uint32_t &b0,
+                                           uint32_t &b1, uint32_t &rare, uint32_t bit) {
+  const bool lt0 = v < Lf[0], lt1 = v < Lf[1];
+  b0 += lt0 ? 1u : 0u;
+  b1 += lt1 ? 1u : 0u;
+  const bool in0 = !lt0 && (v <= Uf[0]);
+  const bool in1 = !lt1 && (v <= Uf[1]);
+  const bool fin = fabsf(v) < __int_as_float(0x7F800000);
+  // NaN: every compare is false, so lt* are false and !lt* && (v <= U) is false as well
+  if (in0 || in1 || !fin) rare |= bit;
 }
 
 template <bool NATIVE>
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_ok) {
-  __shared__ uint32_t s_cand[2][kScanTile];
-  __shared__ uint32_t s_cnt[2];
-  __shared__ uint32_t s_base[2];
-  __shared__ uint32_t s_red[10][kScanThreads / 32];
+  __shared__ ScanShared sh;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   FrameState *fs = kp.state + b;
   const float *frame = kp.depth + (size_t)b * kp.g.D;
   const uint32_t n = kp.g.P;
-  uint32_t L[2], U[2];
-  L[0] = fs->brL[0]; L[1] = fs->brL[1]; U[0] = fs->brU[0]; U[1] = fs->brU[1];
-  if (tid < 2) s_cnt[tid] = 0;
+  float Lf[2], Uf[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const uint32_t L = fs->brL[br], U = fs->brU[br];
+    Lf[br] = (L == 0u) ? -__int_as_float(0x7F800000) : key_to_float(L);           // open below
+    Uf[br] = (U == 0xFFFFFFFFu) ? __int_as_float(0x7F800000) : key_to_float(U);   // open above
+  }
+  if (tid < 2) { sh.cnt[tid] = 0; sh.eqL[tid] = 0; sh.eqU[tid] = 0; }
+  if (tid == 2) { sh.nf = 0; sh.nan = 0; }
   __syncthreads();
-  ScanAcc a;
-  a.below[0] = a.below[1] = a.eqL[0] = a.eqL[1] = a.eqU[0] = a.eqU[1] = 0;
-  a.nf = a.nan = 0; a.mn = 0xFFFFFFFFu; a.mx = 0u;
+  uint32_t b0 = 0, b1 = 0, rare = 0;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
+  // element e (0..15) of this thread is pixel tile_base + 4*((e>>2)*kScanThreads + tid) + (e&3)
 
   if (NATIVE) {
     float4 r[kScanPerThread / 4];
@@ -150,13 +188,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
     for (int j = 0; j < kScanPerThread / 4; ++j) {
       uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
       if (full[j]) {
-        scan_value(r[j].x, L, U, a, s_cand, s_cnt);
-        scan_value(r[j].y, L, U, a, s_cand, s_cnt);
-        scan_value(r[j].z, L, U, a, s_cand, s_cnt);
-        scan_value(r[j].w, L, U, a, s_cand, s_cnt);
+        scan_value(r[j].x, Lf, Uf, b0, b1, rare, 1u << (4 * j + 0));
+        scan_value(r[j].y, Lf, Uf, b0, b1, rare, 1u << (4 * j + 1));
+        scan_value(r[j].z, Lf, Uf, b0, b1, rare, 1u << (4 * j + 2));
+        scan_value(r[j].w, Lf, Uf, b0, b1, rare, 1u << (4 * j + 3));
       } else {
         for (uint32_t k = 0; k < 4u; ++k)
-          if (p + k < n) scan_value(__ldg(frame + p + k), L, U, a, s_cand, s_cnt);
+          if (p + k < n) scan_value(__ldg(frame + p + k), Lf, Uf, b0, b1, rare, 1u << (4 * j + k));
       }
     }
   } else {
@@ -175,52 +213,45 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
           ty = axis_tap((int32_t)v, kp.g.scale_y, kp.g.h);
         }
         AxisTap tx = axis_tap((int32_t)u, kp.g.scale_x, kp.g.w);
-        scan_value(bilinear_sample(frame, kp.g.w, tx, ty), L, U, a, s_cand, s_cnt);
+        scan_value(bilinear_sample(frame, kp.g.w, tx, ty), Lf, Uf, b0, b1, rare, 1u << (4 * j + k));
         u += 1;
       }
     }
   }
+  // rare elements: re-read (L2 hit) or recompute the value and classify it exactly
+  while (rare) {
+    const int e = __ffs(rare) - 1;
+    rare &= rare - 1u;
+    const uint32_t p = tile_base + 4u * (uint32_t)((e >> 2) * kScanThreads + tid) + (uint32_t)(e & 3);
+    scan_rare(depth_at<NATIVE>(frame, kp.g, p), Lf, Uf, sh);
+  }
 
-  // CTA reduction of the ten counters, then one global atomic each
+  // CTA reduction of the two "below" counters; everything else already sits in shared memory
   const int lane = tid & 31, warp = tid >> 5;
-  uint32_t vals[10] = {a.below[0], a.below[1], a.eqL[0], a.eqL[1], a.eqU[0], a.eqU[1], a.nf, a.nan, a.mn, a.mx};
-#pragma unroll
-  for (int c = 0; c < 10; ++c) {
-    uint32_t r = (c == 8) ? warp_min(vals[c]) : (c == 9) ? warp_max(vals[c]) : warp_sum(vals[c]);
-    if (lane == 0) s_red[c][warp] = r;
-  }
+  b0 = warp_sum(b0);
+  b1 = warp_sum(b1);
+  if (lane == 0) { sh.red[0][warp] = b0; sh.red[1][warp] = b1; }
   __syncthreads();
-  if (tid < 10) {
-    uint32_t r = s_red[tid][0];
-    for (int w = 1; w < kScanThreads / 32; ++w) {
-      uint32_t x = s_red[tid][w];
-      r = (tid == 8) ? min(r, x) : (tid == 9) ? max(r, x) : r + x;
-    }
-    switch (tid) {
-      case 0: if (r) atomicAdd(&fs->below[0], r); break;
-      case 1: if (r) atomicAdd(&fs->below[1], r); break;
-      case 2: if (r) atomicAdd(&fs->eqL[0], r); break;
-      case 3: if (r) atomicAdd(&fs->eqL[1], r); break;
-      case 4: if (r) atomicAdd(&fs->eqU[0], r); break;
-      case 5: if (r) atomicAdd(&fs->eqU[1], r); break;
-      case 6: if (r) atomicAdd(&fs->n_nonfinite, r); break;
-      case 7: if (r) atomicAdd(&fs->n_nan, r); break;
-      case 8: if (r != 0xFFFFFFFFu) atomicMin(&fs->min_key, r); break;
-      case 9: if (r != 0u) atomicMax(&fs->max_key, r); break;
-    }
-  }
-  // flush this tile's candidates: one reservation per bracket per CTA
   if (tid < 2) {
-    uint32_t c = s_cnt[tid];
-    s_base[tid] = c ? atomicAdd(&fs->inside[tid], c) : 0u;
+    uint32_t r = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) r += sh.red[tid][w];
+    if (r) atomicAdd(&fs->below[tid], r);
+    if (sh.eqL[tid]) atomicAdd(&fs->eqL[tid], sh.eqL[tid]);
+    if (sh.eqU[tid]) atomicAdd(&fs->eqU[tid], sh.eqU[tid]);
+    const uint32_t c = sh.cnt[tid];
+    sh.base[tid] = c ? atomicAdd(&fs->inside[tid], c) : 0u;
+  }
+  if (tid == 2) {
+    if (sh.nf) atomicAdd(&fs->n_nonfinite, sh.nf);
+    if (sh.nan) atomicAdd(&fs->n_nan, sh.nan);
   }
   __syncthreads();
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
-    const uint32_t c = s_cnt[br], base = s_base[br];
+    const uint32_t c = sh.cnt[br], base = sh.base[br];
     uint32_t *dst = kp.cand + ((size_t)b * 2 + br) * kp.cand_cap;
     for (uint32_t i = tid; i < c; i += kScanThreads)
-      if (base + i < kp.cand_cap) dst[base + i] = s_cand[br][i];
+      if (base + i < kp.cand_cap) dst[base + i] = sh.cand[br][i];
   }
 }
 
@@ -242,18 +273,24 @@ __device__ void finalise_fast(FrameState *fs, uint32_t n) {
   RankPair r2 = percentile_ranks(n, D2PC_Q02), r98 = percentile_ranks(n, D2PC_Q98);
   double p2 = lerp_percentile(key_to_float(vfs->sel_key[0]), key_to_float(vfs->sel_key[1]), r2.gamma);
   double p98 = lerp_percentile(key_to_float(vfs->sel_key[2]), key_to_float(vfs->sel_key[3]), r98.gamma);
+  if (!(p98 > p2)) {  // degenerate percentiles need min/max: the exact path computes them
+    vfs->status = D2PC_FRAME_NEEDS_FALLBACK;
+    return;
+  }
   NormParams np_;
-  finalise_norm(p2, p98, key_to_float(vfs->min_key), key_to_float(vfs->max_key), false, &np_);
+  finalise_norm(p2, p98, 0.0f, 0.0f, false, &np_);
   np_.median = 0.0f;
   np_.has_nonfinite = 0;
+  finish_norm(&np_);
   fs->norm = np_;
   __threadfence();
   vfs->status = D2PC_FRAME_READY;
 }
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
-  extern __shared__ uint32_t sk[];  // kSortCap keys
-  __shared__ uint32_t s_n2, s_below2, s_L2, s_U2;
+  extern __shared__ uint32_t sk[];  // kSelCap keys
+  __shared__ uint32_t s_n2, s_below2;
+  __shared__ uint32_t s_cnt[3 * 2];
   const int br = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   FrameState *fs = kp.state + b;
   const uint32_t n = kp.g.P;
@@ -278,62 +315,65 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
   }
   const bool any_need = need[0] >= 0 || need[1] >= 0;
   if (nin > cap && any_need) fail = true;
+  if (tid < 6) s_cnt[tid] = 0;
+  if (tid == 0) { s_n2 = 0; s_below2 = 0; }
+  __syncthreads();
 
   if (!fail && any_need) {
-    if (nin <= (uint32_t)kSortCap) {
-      const uint32_t np2 = next_pow2(nin < 2u ? 2u : nin);
-      for (uint32_t i = tid; i < np2; i += blockDim.x) sk[i] = i < nin ? cand[i] : 0xFFFFFFFFu;
-      __syncthreads();
-      block_bitonic_sort(sk, np2);
-      for (int t = 0; t < 2; ++t)
-        if (need[t] >= 0) key[t] = sk[need[t]];
+    uint32_t n_keys = nin, base_rank = 0;
+    if (nin <= (uint32_t)kSelCap) {
+      for (uint32_t i = tid; i < nin; i += blockDim.x) sk[i] = cand[i];
     } else {
-      // level 2: sample the candidate list, bracket the wanted ranks, collect, sort
+      // level 2: sample the candidate list (4 keys per thread), bracket the wanted ranks,
+      // then collect the candidates inside that bracket into shared memory
+      constexpr int E2 = kSample2Size / kSelThreads;
       const uint32_t S2 = kSample2Size;
-      for (uint32_t j = tid; j < S2; j += blockDim.x) {
+      uint32_t k2[E2];
+#pragma unroll
+      for (int e = 0; e < E2; ++e) {
+        const uint32_t j = (uint32_t)e * kSelThreads + (uint32_t)tid;
         uint32_t start = (uint32_t)(((unsigned long long)j * nin) / S2);
         uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * nin) / S2);
         uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)(b * 2 + br) * 0xC2B2AE35u + 99u) % (end - start);
-        sk[j] = cand[idx];
+        k2[e] = cand[idx];
       }
-      if (tid == 0) { s_n2 = 0; s_below2 = 0; }
-      __syncthreads();
-      block_bitonic_sort(sk, S2);
-      long long rlo = need[0] >= 0 ? need[0] : need[1];
-      long long rhi = need[1] >= 0 ? need[1] : need[0];
-      if (tid == 0) {
-        double q2 = (double)rlo / (double)nin;
-        int32_t m2 = bracket_margin(q2, (int)S2);
-        long long iL = (long long)(((unsigned long long)rlo * S2) / nin) - m2;
-        long long iU = (long long)(((unsigned long long)rhi * S2) / nin) + 1 + m2;
-        s_L2 = iL < 0 ? 0u : sk[iL];
-        s_U2 = iU >= (long long)S2 ? 0xFFFFFFFFu : sk[iU];
-      }
-      __syncthreads();
-      const uint32_t L2 = s_L2, U2 = s_U2;
+      const long long rlo = need[0] >= 0 ? need[0] : need[1];
+      const long long rhi = need[1] >= 0 ? need[1] : need[0];
+      const double q2 = (double)rlo / (double)nin;
+      const int32_t m2 = bracket_margin(q2, (int)S2);
+      const long long iL = (long long)(((unsigned long long)rlo * S2) / nin) - m2;
+      const long long iU = (long long)(((unsigned long long)rhi * S2) / nin) + 1 + m2;
+      uint32_t r2[2] = {iL < 0 ? 0u : (uint32_t)iL, iU >= (long long)S2 ? S2 - 1 : (uint32_t)iU};
+      uint32_t o2[2];
+      block_select_regs<E2, 2>(k2, r2, o2, s_cnt);
+      const uint32_t L2 = iL < 0 ? 0u : o2[0];
+      const uint32_t U2 = iU >= (long long)S2 ? 0xFFFFFFFFu : o2[1];
       uint32_t my_below = 0;
       for (uint32_t i = tid; i < nin; i += blockDim.x) {
         uint32_t k = cand[i];
         if (k < L2) my_below++;
         else if (k <= U2) {
           uint32_t pos = atomicAdd(&s_n2, 1u);
-          if (pos < (uint32_t)kSortCap) sk[pos] = k;
+          if (pos < (uint32_t)kSelCap) sk[pos] = k;
         }
       }
       my_below = warp_sum(my_below);
       if ((tid & 31) == 0 && my_below) atomicAdd(&s_below2, my_below);
       __syncthreads();
-      const uint32_t n2 = s_n2, below2 = s_below2;
-      if (n2 > (uint32_t)kSortCap || (uint32_t)rlo < below2 || (uint32_t)rhi >= below2 + n2) {
-        fail = true;
-      } else {
-        const uint32_t np2 = next_pow2(n2 < 2u ? 2u : n2);
-        for (uint32_t i = n2 + tid; i < np2; i += blockDim.x) sk[i] = 0xFFFFFFFFu;
-        __syncthreads();
-        block_bitonic_sort(sk, np2);
-        for (int t = 0; t < 2; ++t)
-          if (need[t] >= 0) key[t] = sk[need[t] - below2];
-      }
+      n_keys = s_n2;
+      base_rank = s_below2;
+      if (n_keys > (uint32_t)kSelCap || (uint32_t)rlo < base_rank || (uint32_t)rhi >= base_rank + n_keys) fail = true;
+      // block_bisect's counters: all rounds of the level-2 select ended on a barrier, but the
+      // rotating buffers may hold residue -> clear again before the final select
+      if (tid < 6) s_cnt[tid] = 0;
+    }
+    __syncthreads();
+    if (!fail) {
+      uint32_t rk[2], ok[2];
+      for (int t = 0; t < 2; ++t) rk[t] = need[t] >= 0 ? (uint32_t)need[t] - base_rank : 0u;
+      block_select_smem<2>(sk, n_keys, rk, ok, s_cnt);
+      for (int t = 0; t < 2; ++t)
+        if (need[t] >= 0) key[t] = ok[t];
     }
   }
 
@@ -395,6 +435,7 @@ __global__ void __launch_bounds__(kScanThreads) fb_hist_kernel(KParams kp, int s
   __syncthreads();
   const int shift = 24 - 8 * pass;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
   for (int j = 0; j < kScanPerThread; ++j) {
     uint32_t p = tile_base + (uint32_t)(j * kScanThreads + tid);
     if (p >= n) break;
@@ -405,9 +446,19 @@ __global__ void __launch_bounds__(kScanThreads) fb_hist_kernel(KParams kp, int s
       if (!is_finite_f32(v)) v = med;  // np.where(finite, d, med)
     }
     uint32_t key = float_to_key(v);
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
     for (int t = 0; t < T; ++t) {
       bool match = (pass == 0) || ((key >> (shift + 8)) == (prefix[t] >> (shift + 8)));
       if (match) atomicAdd(&sh[t][(key >> shift) & 255u], 1u);
+    }
+  }
+  if (stage == kStagePercentile && pass == 0) {  // d.min() / d.max() of the repaired map
+    kmin = warp_min(kmin);
+    kmax = warp_max(kmax);
+    if ((tid & 31) == 0) {
+      if (kmin != 0xFFFFFFFFu) atomicMin(&fs->min_key, kmin);
+      if (kmax != 0u) atomicMax(&fs->max_key, kmax);
     }
   }
   __syncthreads();
@@ -487,16 +538,12 @@ __global__ void fb_finalise_kernel(KParams kp) {
     RankPair r2 = percentile_ranks(n, D2PC_Q02), r98 = percentile_ranks(n, D2PC_Q98);
     double p2 = lerp_percentile(key_to_float(fs->fb_prefix[0]), key_to_float(fs->fb_prefix[1]), r2.gamma);
     double p98 = lerp_percentile(key_to_float(fs->fb_prefix[2]), key_to_float(fs->fb_prefix[3]), r98.gamma);
-    uint32_t kmin = fs->min_key, kmax = fs->max_key;  // over finite values (0xFFFFFFFF / 0: none)
-    if (has_nf) {
-      uint32_t km = float_to_key(med);
-      kmin = min(kmin, km);
-      kmax = max(kmax, km);
-    }
+    const uint32_t kmin = fs->min_key, kmax = fs->max_key;  // of the repaired map (stage P, pass 0)
     finalise_norm(p2, p98, key_to_float(kmin), key_to_float(kmax), false, &np_);
   }
   np_.median = med;
   np_.has_nonfinite = has_nf;
+  finish_norm(&np_);
   fs->norm = np_;
   __threadfence();
   fs->status = D2PC_FRAME_READY;
@@ -552,13 +599,11 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   KParams kp = make_kparams(*cfg, d_depth, d_workspace);
-  const size_t sample_smem = (size_t)kSampleSize * sizeof(uint32_t);
-  const size_t select_smem = (size_t)kSortCap * sizeof(uint32_t);
-  static bool attr_done = false;
-  if (!attr_done) {
+  const size_t sample_smem = 0;
+  const size_t select_smem = (size_t)kSelCap * sizeof(uint32_t);
+  {
     cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem);
     if (e != cudaSuccess) return record_cuda_error(e);
-    attr_done = true;
   }
   const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)d_depth & 15u) == 0u);
   dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);

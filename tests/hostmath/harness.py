@@ -32,7 +32,8 @@ def load():
     return lib
 
 
-def run_stage(lib, image, depth, density="medium", invert=True, depth_scale=10.0, fov=None):
+def run_stage(lib, image, depth, density="medium", invert=True, depth_scale=10.0, fov=None, simple=False):
+    lib.hm_set_simple(1 if simple else 0)
     from image_to_pointcloud_b200.engine import DENSITY_STEP, reference_intrinsics
     H, W = image.shape[:2]
     h, w = depth.shape[:2]

@@ -13,7 +13,13 @@
 
 using namespace d2pc;
 
+static int g_use_simple = 0;
+static int g_last_simple = 0;
+
 extern "C" {
+
+void hm_set_simple(int on) { g_use_simple = on; }
+int hm_last_simple(void) { return g_last_simple; }
 
 int hm_resize(const float *src, int h, int w, float *dst, int H, int W) {
   const double sx = (double)w / (double)W, sy = (double)h / (double)H;
@@ -75,10 +81,19 @@ long hm_depth_to_point_cloud(const uint8_t *img, int H, int W, int C, const floa
   PixelConsts pc;
   pc.scale = scale; pc.cx = cx; pc.cy = cy; pc.f = f; pc.inv_f = 1.0 / f; pc.invert = invert;
   long i = 0;
+  finish_norm(&fin);
+  const NormParams &sn = fin;
+  const bool simple = g_use_simple && fin.simple && consts_simple(pc);
+  g_last_simple = simple ? 1 : 0;
   for (int v = 0; v < H; v += step)
     for (int u = 0; u < W; u += step, ++i) {
-      double n = normalised_depth(d[(size_t)v * W + u], fin, invert);
-      back_project(n, u, v, pc, &xyz[3 * i], &xyz[3 * i + 1], &xyz[3 * i + 2]);
+      if (simple) {  // the guard-free straight-line path the emit_fast kernel takes
+        simple_point(d[(size_t)v * W + u], (double)u - cx, (double)v - cy, sn, pc, &xyz[3 * i], &xyz[3 * i + 1],
+                     &xyz[3 * i + 2]);
+      } else {
+        double n = normalised_depth(d[(size_t)v * W + u], fin, invert);
+        back_project(n, u, v, pc, &xyz[3 * i], &xyz[3 * i + 1], &xyz[3 * i + 2]);
+      }
       if (C >= 3) {
         const uint8_t *cp = img + ((size_t)v * W + u) * C;
         rgb[3 * i] = cp[2]; rgb[3 * i + 1] = cp[1]; rgb[3 * i + 2] = cp[0];

@@ -36,21 +36,45 @@ def test_resize_matches_oracle(hm):
         assert_bits_equal(out, O.resize_bilinear(d, dh[0], dh[1]), f"resize {sh}->{dh}")
 
 
-def test_small_goldens_bit_exact(hm, small_golden):
+@pytest.mark.parametrize("simple", [False, True])
+def test_small_goldens_bit_exact(hm, small_golden, simple):
+    """simple=True routes eligible frames through the guard-free straight-line path
+    (make_simple_norm / simple_point) that emit_fast_kernel runs; both must match the reference."""
+    n_simple = 0
     for name in small_golden.names:
         img, dep, kw, pts, cols = small_golden.case(name)
         if dep.shape[:2] != img.shape[:2] and min(dep.shape[:2]) < 2:
             continue
-        p, c = harness.run_stage(hm, img, dep, **kw)
+        p, c = harness.run_stage(hm, img, dep, simple=simple, **kw)
+        n_simple += hm.hm_last_simple()
         assert_bits_equal(p, pts, f"{name} points")
         assert_bits_equal(c, cols, f"{name} colors")
+    assert (n_simple >= 14) if simple else (n_simple == 0)
+
+
+def test_simple_path_equals_generic_path_exactly(hm):
+    """Same bits INCLUDING the sign of zero (no canonicalisation): zeros at the clip bound,
+    -0.0 inputs, negative depth_scale, centre column/row."""
+    rng = np.random.default_rng(77)
+    for t in range(40):
+        H, W = int(rng.integers(2, 40)), int(rng.integers(2, 50))
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        dep = (rng.standard_normal((H, W)) * rng.choice([1e-3, 1.0, 1e5])).astype(np.float32)
+        if t % 2 == 0:
+            dep = np.maximum(dep, 0)          # ReLU zeros: p2 == 0.0
+        if t % 3 == 0:
+            dep[dep == 0] = -0.0
+        kw = dict(density="high", invert=bool(t % 4 < 2), depth_scale=float(rng.choice([10.0, -2.5, 1e-3])))
+        a = harness.run_stage(hm, img, dep, simple=False, **kw)[0]
+        b = harness.run_stage(hm, img, dep, simple=True, **kw)[0]
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), t
 
 
 @pytest.mark.parametrize("name", ["c1_480p_high", "c1_480p_low_noinv", "c2_1080p_dav2", "c2_1080p_scene_nonfinite"])
 def test_large_goldens_sha(hm, large_golden, name):
     g = large_golden["cases"][name]
     img, dep, kw = cases.build_case(cases.LARGE_CASES[name])
-    p, c = harness.run_stage(hm, img, dep, **kw)
+    p, c = harness.run_stage(hm, img, dep, simple=True, **kw)
     assert hashlib.sha256(p.tobytes()).hexdigest() == g["points_sha256"]
     assert hashlib.sha256(c.tobytes()).hexdigest() == g["colors_sha256"]
 
