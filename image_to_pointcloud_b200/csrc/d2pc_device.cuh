@@ -16,7 +16,7 @@ namespace d2pc {
 constexpr int kSampleSize = 8192;      // level-1 sample per frame (stratified), power of two
 constexpr int kSample2Size = 4096;     // level-2 sample over a bracket's candidates
 constexpr int kSortCap = 16384;        // frames with at most this many pixels skip sampling
-constexpr int kSelCap = 49152;         // keys one select CTA can hold in shared memory (192 KB)
+constexpr int kSelBits = 12;           // bucket histogram levels of the exact selection: 4096 bins
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 16;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // 4096 pixels per CTA
@@ -207,62 +207,110 @@ __device__ __forceinline__ void block_bitonic_sort(uint32_t *s, uint32_t n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact order statistics without sorting: bisection on the key bits.  For every target t,
-// out[t] = the rank[t]-th smallest key (0-based) among all keys the CTA holds.  32 rounds, each
-// a counting pass (key < trial) + one barrier; T targets share the passes.  s_cnt: 3*T words of
-// shared memory, zeroed by the caller (followed by a barrier).  Every thread gets the results.
+// Exact order statistics without sorting: multi-level bucket histogram over the key range.
+// For every target t, out[t] = the rank[t]-th smallest key (0-based) among the keys the CTA
+// visits through `for_each(f)` (f is called once per key owned by the calling thread; the
+// functor must visit the same keys on every call).  Level 1 splits the common range [lo0, hi0]
+// into 2^NBLOG equal power-of-two buckets and locates each target's bucket by a block scan;
+// the next level does the same inside that bucket, until the bucket width is one key.  At most
+// ceil(32 / NBLOG) passes; keys spread over the range give conflict-free shared atomics.
+//   s_hist: T << NBLOG words;  s_res: 2*T + 40 words.  All threads must call; every thread
+//   gets the results.  A rank outside the population returns ok = false.
 // ------------------------------------------------------------------------------------------
-template <int T, typename CountFn>
-__device__ __forceinline__ void block_bisect(const uint32_t (&rank)[T], uint32_t (&out)[T], uint32_t *s_cnt,
-                                             CountFn count_below) {
-  uint32_t K[T];
+template <int T, int NBLOG, typename ForEach>
+__device__ __forceinline__ bool block_hist_select(ForEach for_each, uint32_t lo0, uint32_t hi0,
+                                                  const uint32_t (&rank)[T], uint32_t (&out)[T],
+                                                  uint32_t *s_hist, uint32_t *s_res) {
+  constexpr uint32_t NB = 1u << NBLOG;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  uint32_t lo[T], span[T], base[T];
+  bool done[T];
 #pragma unroll
-  for (int t = 0; t < T; ++t) K[t] = 0u;
-  int buf = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    uint32_t trial[T], c[T];
+  for (int t = 0; t < T; ++t) { lo[t] = lo0; span[t] = hi0 - lo0; base[t] = 0; done[t] = false; out[t] = 0; }
+  bool shared_range = true, ok = true;
+  uint32_t *s_warp = s_res + 2 * T;  // [<= 32] warp totals
+  for (int level = 0; level < 6; ++level) {
+    bool all_done = true;
 #pragma unroll
-    for (int t = 0; t < T; ++t) { trial[t] = K[t] | (1u << bit); c[t] = 0u; }
-    count_below(trial, c);  // c[t] += number of this thread's keys < trial[t]
+    for (int t = 0; t < T; ++t) all_done = all_done && done[t];
+    if (all_done) break;
+    int shift[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      c[t] = warp_sum(c[t]);
-      if ((threadIdx.x & 31) == 0 && c[t]) atomicAdd(&s_cnt[buf * T + t], c[t]);
+      const int bits = span[t] ? 32 - __clz(span[t]) : 0;
+      shift[t] = bits > NBLOG ? bits - NBLOG : 0;
+    }
+    const int nh = shared_range ? 1 : T;
+    for (uint32_t i = tid; i < (uint32_t)nh * NB; i += nthr) s_hist[i] = 0u;
+    if (tid < 2 * T) s_res[tid] = 0xFFFFFFFFu;
+    __syncthreads();
+    if (shared_range) {
+      for_each([&](uint32_t key) {
+        const uint32_t d = key - lo[0];
+        if (d <= span[0]) atomicAdd(&s_hist[d >> shift[0]], 1u);
+      });
+    } else {
+      for_each([&](uint32_t key) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const uint32_t d = key - lo[t];
+          if (!done[t] && d <= span[t]) atomicAdd(&s_hist[t * NB + (d >> shift[t])], 1u);
+        }
+      });
+    }
+    __syncthreads();
+    // locate each target's bucket: block-wide exclusive scan of every live histogram
+    for (int h = 0; h < nh; ++h) {
+      if (!shared_range && done[h]) continue;  // uniform
+      const uint32_t *hist = s_hist + (size_t)h * NB;
+      constexpr int PER = 4;  // consecutive bins per thread per chunk
+      uint32_t carry = 0;
+      for (uint32_t chunk = 0; chunk < NB; chunk += (uint32_t)nthr * PER) {
+        const uint32_t b0 = chunk + (uint32_t)tid * PER;
+        uint32_t c[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { c[i] = (b0 + i < NB) ? hist[b0 + i] : 0u; sum += c[i]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+        for (int w = 0; w < nwarp; ++w) { const uint32_t x = s_warp[w]; if (w < warp) woff += x; total += x; }
+        uint32_t pref = carry + woff + incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const bool mine = shared_range ? !done[t] : (t == h);
+            const uint32_t r = rank[t] - base[t];
+            if (mine && c[i] && pref <= r && r < pref + c[i]) { s_res[2 * t] = b0 + i; s_res[2 * t + 1] = pref; }
+          }
+          pref += c[i];
+        }
+        carry += total;
+        __syncthreads();
+      }
     }
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < T; ++t)
-      if (s_cnt[buf * T + t] <= rank[t]) K[t] = trial[t];
-    // the buffer used two rounds from now was last read one round ago: safe to clear here
-    const int clr = (buf + 2) % 3;
-    if (threadIdx.x < T) s_cnt[clr * T + threadIdx.x] = 0u;
-    buf = (buf + 1) % 3;
-  }
-#pragma unroll
-  for (int t = 0; t < T; ++t) out[t] = K[t];
-}
-
-template <int E, int T>
-__device__ __forceinline__ void block_select_regs(const uint32_t (&k)[E], const uint32_t (&rank)[T],
-                                                  uint32_t (&out)[T], uint32_t *s_cnt) {
-  block_bisect<T>(rank, out, s_cnt, [&](const uint32_t (&trial)[T], uint32_t (&c)[T]) {
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-#pragma unroll
-      for (int t = 0; t < T; ++t) c[t] += (k[e] < trial[t]) ? 1u : 0u;
-  });
-}
-
-template <int T>
-__device__ __forceinline__ void block_select_smem(const uint32_t *sk, uint32_t n, const uint32_t (&rank)[T],
-                                                  uint32_t (&out)[T], uint32_t *s_cnt) {
-  block_bisect<T>(rank, out, s_cnt, [&](const uint32_t (&trial)[T], uint32_t (&c)[T]) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t key = sk[i];
-#pragma unroll
-      for (int t = 0; t < T; ++t) c[t] += (key < trial[t]) ? 1u : 0u;
+    for (int t = 0; t < T; ++t) {
+      if (done[t]) continue;
+      const uint32_t bin = s_res[2 * t], pref = s_res[2 * t + 1];
+      if (bin == 0xFFFFFFFFu) { ok = false; done[t] = true; continue; }
+      base[t] += pref;
+      lo[t] += bin << shift[t];
+      span[t] = shift[t] ? ((1u << shift[t]) - 1u) : 0u;
+      if (shift[t] == 0) { done[t] = true; out[t] = lo[t]; }
     }
-  });
+    shared_range = false;
+    __syncthreads();
+  }
+  return ok;
 }
 
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32

@@ -4,15 +4,14 @@
 //
 // Fast path (3 launches per batch, depth map read from HBM exactly once):
 //   sample_kernel  1 CTA/frame   stratified sample (registers) -> exact sample order statistics
-//                                by bisection on the key bits -> key brackets [L, U] that
-//                                contain the wanted ranks with ~6 sigma margin
+//                                by a multi-level bucket histogram -> key brackets [L, U]
+//                                that contain the wanted ranks with ~6 sigma margin
 //   scan_kernel    streaming     per key: count below / equal-to-bound, append the few keys
 //                                strictly inside a bracket (about 2% each) to a candidate list,
 //                                min/max, non-finite counts.  Pure compares, no histogram:
 //                                the only atomics are per CTA.
-//   select_kernel  2 CTA/frame   exact rank selection inside the candidate list (bisection over
-//                                the keys in smem; a second sample/bracket level first when
-//                                the list does not fit), then
+//   select_kernel  2 CTA/frame   exact rank selection inside the candidate list (multi-level
+//                                bucket histogram, 2-3 passes over the L2-resident list), then
 //                                the last CTA of a frame evaluates NumPy's _lerp in float64
 //                                and writes the parameter block.
 // Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, candidate
@@ -32,15 +31,16 @@ __device__ __forceinline__ int32_t bracket_margin(double q, int S) {
 // ------------------------------------------------------------------------------------------
 template <bool NATIVE>
 __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
-  __shared__ uint32_t s_bad;
-  __shared__ uint32_t s_cnt[3 * 4];
+  extern __shared__ uint32_t s_hist[];  // 4 << kSelBits words
+  __shared__ uint32_t s_bad, s_min, s_max;
+  __shared__ uint32_t s_res[2 * 4 + 40];
   const int b = blockIdx.x;
   FrameState *fs = kp.state + b;
   const float *frame = kp.depth + (size_t)b * kp.g.D;
   const uint32_t n = kp.g.P;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    s_bad = 0;
+    s_bad = 0; s_min = 0xFFFFFFFFu; s_max = 0u;
     for (int i = 0; i < 2; ++i) {
       fs->below[i] = 0; fs->eqL[i] = 0; fs->inside[i] = 0; fs->eqU[i] = 0;
     }
@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     fs->norm.median = 0.0f;
     fs->norm.simple = 0;
   }
-  if (tid < 12) s_cnt[tid] = 0;
   if (n <= (uint32_t)kSortCap) {  // small frame: every finite key is a candidate
     if (tid == 0) {
       fs->brL[0] = fs->brL[1] = 0u;
@@ -78,7 +77,15 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     k[e] = 0xFFFFFFFFu;
     if (is_finite_f32(v)) k[e] = float_to_key(v); else bad = true;
   }
+  __syncthreads();
   if (bad) atomicOr(&s_bad, 1u);
+  {  // key range of the sample (makes the first histogram level adaptive)
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { mn = min(mn, k[e]); mx = max(mx, k[e]); }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if ((tid & 31) == 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
+  }
   __syncthreads();
   // sample ranks that bracket the wanted order statistics with a ~6 sigma margin
   uint32_t rank[4], out[4];
@@ -96,7 +103,10 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     rank[2 * br + 0] = open_lo[br] ? 0u : (uint32_t)iL;
     rank[2 * br + 1] = open_hi[br] ? S - 1 : (uint32_t)iU;
   }
-  block_select_regs<E, 4>(k, rank, out, s_cnt);
+  block_hist_select<4, kSelBits>([&](auto f) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) f(k[e]);
+  }, s_min, s_max, rank, out, s_hist, s_res);
   if (tid < 2) {
     fs->brL[tid] = open_lo[tid] ? 0u : out[2 * tid + 0];
     fs->brU[tid] = open_hi[tid] ? 0xFFFFFFFFu : out[2 * tid + 1];
@@ -115,6 +125,7 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
 // fallback, which computes them.
 struct ScanShared {
   uint32_t cand[2][kScanTile];
+  float queue[kScanPerThread][kScanThreads];  // per-thread deferred ("rare") values, slot-major
   uint32_t cnt[2], eqL[2], eqU[2], nf, nan;
   uint32_t base[2];
   uint32_t red[2][kScanThreads / 32];
@@ -138,24 +149,38 @@ __device__ __forceinline__ void scan_rare(float v, const float Lf[2], const floa
   }
 }
 
-// Common path: count "below", and only FLAG the element (bit `bit` of `rare`) when it is inside a
-// bracket or non-finite.  Flagged elements (about 4%) are handled after the streaming loop, so
-// the hot loop has no divergent branch.
+// Common path, 11 predicated instructions, no branch: count "below" for both brackets and, when
+// the value is inside a bracket or non-finite (about 4% of pixels), push it on the thread's
+// private queue in shared memory (qaddr = shared-space byte address of the next free slot).
+// Queued values are classified exactly after the streaming loop.
+// NaN: every ordered compare is false; setp.gtu (unordered greater) is true -> queued.
 __device__ __forceinline__ void scan_value(float v, const float Lf[2], const float Uf[2], uint32_t &b0,
-                                           uint32_t &b1, uint32_t &rare, uint32_t bit) {
-  const bool lt0 = v < Lf[0], lt1 = v < Lf[1];
-  b0 += lt0 ? 1u : 0u;
-  b1 += lt1 ? 1u : 0u;
-  const bool in0 = !lt0 && (v <= Uf[0]);
-  const bool in1 = !lt1 && (v <= Uf[1]);
-  const bool fin = fabsf(v) < __int_as_float(0x7F800000);
-  // NaN: every compare is false, so lt* are false and !lt* && (v <= U) is false as well
-  if (in0 || in1 || !fin) rare |= bit;
+                                           uint32_t &b1, uint32_t &qaddr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred lt0, lt1, in0, any;\n\t"
+      ".reg .f32 av;\n\t"
+      "setp.lt.f32 lt0, %3, %4;\n\t"
+      "setp.lt.f32 lt1, %3, %5;\n\t"
+      "@lt0 add.u32 %0, %0, 1;\n\t"
+      "@lt1 add.u32 %1, %1, 1;\n\t"
+      "setp.le.and.f32 in0, %3, %6, !lt0;\n\t"
+      "setp.le.and.f32 any, %3, %7, !lt1;\n\t"
+      "or.pred any, any, in0;\n\t"
+      "abs.f32 av, %3;\n\t"
+      "setp.gtu.or.f32 any, av, 0f7F7FFFFF, any;\n\t"
+      "@any st.shared.f32 [%2], %3;\n\t"
+      "@any add.u32 %2, %2, %8;\n\t"
+      "}"
+      : "+r"(b0), "+r"(b1), "+r"(qaddr)
+      : "f"(v), "f"(Lf[0]), "f"(Lf[1]), "f"(Uf[0]), "f"(Uf[1]), "n"(kScanThreads * 4)
+      : "memory");
 }
 
 template <bool NATIVE>
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_ok) {
-  __shared__ ScanShared sh;
+  extern __shared__ __align__(16) unsigned char scan_smem[];
+  ScanShared &sh = *reinterpret_cast<ScanShared *>(scan_smem);
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   FrameState *fs = kp.state + b;
@@ -171,9 +196,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
   if (tid < 2) { sh.cnt[tid] = 0; sh.eqL[tid] = 0; sh.eqU[tid] = 0; }
   if (tid == 2) { sh.nf = 0; sh.nan = 0; }
   __syncthreads();
-  uint32_t b0 = 0, b1 = 0, rare = 0;
+  uint32_t b0 = 0, b1 = 0;
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sh.queue[0][tid]);
+  uint32_t qaddr = q0;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
-  // element e (0..15) of this thread is pixel tile_base + 4*((e>>2)*kScanThreads + tid) + (e&3)
 
   if (NATIVE) {
     float4 r[kScanPerThread / 4];
@@ -188,13 +214,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
     for (int j = 0; j < kScanPerThread / 4; ++j) {
       uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
       if (full[j]) {
-        scan_value(r[j].x, Lf, Uf, b0, b1, rare, 1u << (4 * j + 0));
-        scan_value(r[j].y, Lf, Uf, b0, b1, rare, 1u << (4 * j + 1));
-        scan_value(r[j].z, Lf, Uf, b0, b1, rare, 1u << (4 * j + 2));
-        scan_value(r[j].w, Lf, Uf, b0, b1, rare, 1u << (4 * j + 3));
+        scan_value(r[j].x, Lf, Uf, b0, b1, qaddr);
+        scan_value(r[j].y, Lf, Uf, b0, b1, qaddr);
+        scan_value(r[j].z, Lf, Uf, b0, b1, qaddr);
+        scan_value(r[j].w, Lf, Uf, b0, b1, qaddr);
       } else {
         for (uint32_t k = 0; k < 4u; ++k)
-          if (p + k < n) scan_value(__ldg(frame + p + k), Lf, Uf, b0, b1, rare, 1u << (4 * j + k));
+          if (p + k < n) scan_value(__ldg(frame + p + k), Lf, Uf, b0, b1, qaddr);
       }
     }
   } else {
@@ -213,18 +239,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
           ty = axis_tap((int32_t)v, kp.g.scale_y, kp.g.h);
         }
         AxisTap tx = axis_tap((int32_t)u, kp.g.scale_x, kp.g.w);
-        scan_value(bilinear_sample(frame, kp.g.w, tx, ty), Lf, Uf, b0, b1, rare, 1u << (4 * j + k));
+        scan_value(bilinear_sample(frame, kp.g.w, tx, ty), Lf, Uf, b0, b1, qaddr);
         u += 1;
       }
     }
   }
-  // rare elements: re-read (L2 hit) or recompute the value and classify it exactly
-  while (rare) {
-    const int e = __ffs(rare) - 1;
-    rare &= rare - 1u;
-    const uint32_t p = tile_base + 4u * (uint32_t)((e >> 2) * kScanThreads + tid) + (uint32_t)(e & 3);
-    scan_rare(depth_at<NATIVE>(frame, kp.g, p), Lf, Uf, sh);
-  }
+  // queued values (this thread's own slots: no barrier needed)
+  const uint32_t nq = (qaddr - q0) / (uint32_t)(kScanThreads * 4);
+  for (uint32_t j = 0; j < nq; ++j) scan_rare(sh.queue[j][tid], Lf, Uf, sh);
 
   // CTA reduction of the two "below" counters; everything else already sits in shared memory
   const int lane = tid & 31, warp = tid >> 5;
@@ -288,9 +310,8 @@ __device__ void finalise_fast(FrameState *fs, uint32_t n) {
 }
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
-  extern __shared__ uint32_t sk[];  // kSelCap keys
-  __shared__ uint32_t s_n2, s_below2;
-  __shared__ uint32_t s_cnt[3 * 2];
+  extern __shared__ uint32_t s_hist[];  // 2 << kSelBits words
+  __shared__ uint32_t s_res[2 * 2 + 40];
   const int br = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   FrameState *fs = kp.state + b;
   const uint32_t n = kp.g.P;
@@ -315,66 +336,20 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
   }
   const bool any_need = need[0] >= 0 || need[1] >= 0;
   if (nin > cap && any_need) fail = true;
-  if (tid < 6) s_cnt[tid] = 0;
-  if (tid == 0) { s_n2 = 0; s_below2 = 0; }
-  __syncthreads();
 
-  if (!fail && any_need) {
-    uint32_t n_keys = nin, base_rank = 0;
-    if (nin <= (uint32_t)kSelCap) {
-      for (uint32_t i = tid; i < nin; i += blockDim.x) sk[i] = cand[i];
-    } else {
-      // level 2: sample the candidate list (4 keys per thread), bracket the wanted ranks,
-      // then collect the candidates inside that bracket into shared memory
-      constexpr int E2 = kSample2Size / kSelThreads;
-      const uint32_t S2 = kSample2Size;
-      uint32_t k2[E2];
-#pragma unroll
-      for (int e = 0; e < E2; ++e) {
-        const uint32_t j = (uint32_t)e * kSelThreads + (uint32_t)tid;
-        uint32_t start = (uint32_t)(((unsigned long long)j * nin) / S2);
-        uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * nin) / S2);
-        uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)(b * 2 + br) * 0xC2B2AE35u + 99u) % (end - start);
-        k2[e] = cand[idx];
-      }
-      const long long rlo = need[0] >= 0 ? need[0] : need[1];
-      const long long rhi = need[1] >= 0 ? need[1] : need[0];
-      const double q2 = (double)rlo / (double)nin;
-      const int32_t m2 = bracket_margin(q2, (int)S2);
-      const long long iL = (long long)(((unsigned long long)rlo * S2) / nin) - m2;
-      const long long iU = (long long)(((unsigned long long)rhi * S2) / nin) + 1 + m2;
-      uint32_t r2[2] = {iL < 0 ? 0u : (uint32_t)iL, iU >= (long long)S2 ? S2 - 1 : (uint32_t)iU};
-      uint32_t o2[2];
-      block_select_regs<E2, 2>(k2, r2, o2, s_cnt);
-      const uint32_t L2 = iL < 0 ? 0u : o2[0];
-      const uint32_t U2 = iU >= (long long)S2 ? 0xFFFFFFFFu : o2[1];
-      uint32_t my_below = 0;
-      for (uint32_t i = tid; i < nin; i += blockDim.x) {
-        uint32_t k = cand[i];
-        if (k < L2) my_below++;
-        else if (k <= U2) {
-          uint32_t pos = atomicAdd(&s_n2, 1u);
-          if (pos < (uint32_t)kSelCap) sk[pos] = k;
-        }
-      }
-      my_below = warp_sum(my_below);
-      if ((tid & 31) == 0 && my_below) atomicAdd(&s_below2, my_below);
-      __syncthreads();
-      n_keys = s_n2;
-      base_rank = s_below2;
-      if (n_keys > (uint32_t)kSelCap || (uint32_t)rlo < base_rank || (uint32_t)rhi >= base_rank + n_keys) fail = true;
-      // block_bisect's counters: all rounds of the level-2 select ended on a barrier, but the
-      // rotating buffers may hold residue -> clear again before the final select
-      if (tid < 6) s_cnt[tid] = 0;
-    }
-    __syncthreads();
-    if (!fail) {
-      uint32_t rk[2], ok[2];
-      for (int t = 0; t < 2; ++t) rk[t] = need[t] >= 0 ? (uint32_t)need[t] - base_rank : 0u;
-      block_select_smem<2>(sk, n_keys, rk, ok, s_cnt);
-      for (int t = 0; t < 2; ++t)
-        if (need[t] >= 0) key[t] = ok[t];
-    }
+  if (!fail && any_need) {  // uniform over the CTA
+    // candidates are strictly inside (L, U) in float order; -0.0 == +0.0 there, so when a bound
+    // is a zero the other zero's key can sit one step outside the key interval: widen by one
+    const uint32_t lo0 = L > 0u ? L - 1u : 0u;
+    const uint32_t hi0 = U < 0xFFFFFFFFu ? U + 1u : U;
+    uint32_t rk[2], ok_[2];
+    for (int t = 0; t < 2; ++t) rk[t] = (uint32_t)(need[t] >= 0 ? need[t] : need[1 - t]);
+    const bool ok = block_hist_select<2, kSelBits>([&](auto f) {
+      for (uint32_t i = tid; i < nin; i += blockDim.x) f(__ldg(cand + i));
+    }, lo0, hi0, rk, ok_, s_hist, s_res);
+    if (!ok) fail = true;
+    for (int t = 0; t < 2; ++t)
+      if (need[t] >= 0) key[t] = ok_[t];
   }
 
   if (tid == 0) {
@@ -599,22 +574,31 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   KParams kp = make_kparams(*cfg, d_depth, d_workspace);
-  const size_t sample_smem = 0;
-  const size_t select_smem = (size_t)kSelCap * sizeof(uint32_t);
+  const size_t sample_smem = (size_t)(4u << kSelBits) * sizeof(uint32_t);  // 64 KB
+  const size_t select_smem = (size_t)(2u << kSelBits) * sizeof(uint32_t);  // 32 KB
   {
-    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem);
+    cudaError_t e = kp.g.native
+        ? cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem)
+        : cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem);
     if (e != cudaSuccess) return record_cuda_error(e);
   }
   const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)d_depth & 15u) == 0u);
   dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
+  const size_t scan_smem_bytes = sizeof(ScanShared);
+  {
+    cudaError_t e = kp.g.native
+        ? cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes)
+        : cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes);
+    if (e != cudaSuccess) return record_cuda_error(e);
+  }
   if (kp.g.native) {
     sample_kernel<true><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
-    scan_kernel<true><<<scan_grid, kScanThreads, 0, st>>>(kp, vec_ok);
+    scan_kernel<true><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, vec_ok);
   } else {
     sample_kernel<false><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
-    scan_kernel<false><<<scan_grid, kScanThreads, 0, st>>>(kp, 0);
+    scan_kernel<false><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, 0);
   }
   D2PC_CHECK_LAUNCH();
   select_kernel<<<dim3(2, cfg->batch), kSelThreads, select_smem, st>>>(kp);
