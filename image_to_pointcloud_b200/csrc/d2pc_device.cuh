@@ -67,7 +67,8 @@ struct __align__(256) FrameState {
   uint32_t inside[2];     // finite keys strictly inside (brL, brU); appended to the candidate list
   uint32_t eqU[2];        // finite keys == brU (brU != brL)
   uint32_t n_nonfinite, n_nan;
-  uint32_t min_key, max_key;  // over finite values
+  uint32_t nqueue[2];     // values the scan deferred to the bracket's raw queue (inside it; non-finite -> queue 0)
+  uint32_t min_key, max_key;  // of the repaired map (fallback path only)
   // exact selection
   uint32_t sel_key[4];    // keys at ranks lo2, hi2, lo98, hi98
   uint32_t sel_fail;
@@ -117,7 +118,7 @@ struct KParams {
   int32_t batch;
   const float *depth;       // [batch, h, w]
   FrameState *state;        // [batch]
-  uint32_t *cand;           // [batch][2][cand_cap]
+  uint32_t *cand;           // [batch][2][cand_cap] per-bracket raw queues of deferred values (float bits)
   unsigned long long *tile_state;  // [batch][emit_tiles]
   uint32_t *fb_hist;        // [batch][kFbTargets][256]
   uint32_t cand_cap, emit_tiles;

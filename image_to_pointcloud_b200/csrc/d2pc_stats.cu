@@ -6,17 +6,18 @@
 //   sample_kernel  1 CTA/frame   stratified sample (registers) -> exact sample order statistics
 //                                by a multi-level bucket histogram -> key brackets [L, U]
 //                                that contain the wanted ranks with ~6 sigma margin
-//   scan_kernel    streaming     per key: count below / equal-to-bound, append the few keys
-//                                strictly inside a bracket (about 2% each) to a candidate list,
-//                                min/max, non-finite counts.  Pure compares, no histogram:
-//                                the only atomics are per CTA.
-//   select_kernel  2 CTA/frame   exact rank selection inside the candidate list (multi-level
-//                                bucket histogram, 2-3 passes over the L2-resident list), then
-//                                the last CTA of a frame evaluates NumPy's _lerp in float64
-//                                and writes the parameter block.
-// Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, candidate
-// overflow) are only marked; d2pc_stats_fallback_enqueue runs the input-agnostic exact path
-// (8-bit radix select, nanmedian repair) for those.
+//   scan_kernel    streaming     per pixel, branch-free: count values below each bracket and
+//                                defer the few values inside a bracket (about 2% each) or
+//                                non-finite to the frame's raw queue.  Pure compares, no
+//                                histogram; the only atomics are per CTA.
+//   select_kernel  2 CTA/frame   classify the queued values against the bracket (equal to a
+//                                bound / strictly inside), resolve the wanted ranks, exact
+//                                selection inside the bracket (multi-level bucket histogram over
+//                                the L2-resident queue); the last CTA of a frame evaluates
+//                                NumPy's _lerp in float64 and writes the parameter block.
+// Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, queue
+// overflow, collapsed percentiles) are only marked; d2pc_stats_fallback_enqueue runs the
+// input-agnostic exact path (8-bit radix select, nanmedian repair) for those.
 #include "d2pc_device.cuh"
 
 namespace d2pc {
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     for (int i = 0; i < 2; ++i) {
       fs->below[i] = 0; fs->eqL[i] = 0; fs->inside[i] = 0; fs->eqU[i] = 0;
     }
-    fs->n_nonfinite = 0; fs->n_nan = 0;
+    fs->n_nonfinite = 0; fs->n_nan = 0; fs->nqueue[0] = 0; fs->nqueue[1] = 0;
     fs->min_key = 0xFFFFFFFFu; fs->max_key = 0u;
     for (int i = 0; i < 4; ++i) fs->sel_key[i] = 0;
     fs->sel_fail = 0; fs->sel_done = 0;
@@ -124,36 +125,15 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
 // min/max are not tracked: a frame whose percentiles collapse (p98 <= p2) goes to the exact
 // fallback, which computes them.
 struct ScanShared {
-  uint32_t cand[2][kScanTile];
-  float queue[kScanPerThread][kScanThreads];  // per-thread deferred ("rare") values, slot-major
-  uint32_t cnt[2], eqL[2], eqU[2], nf, nan;
-  uint32_t base[2];
+  float pqueue[kScanPerThread][kScanThreads];  // per-thread deferred values, slot-major
+  uint32_t qtotal[2], gbase[2];
   uint32_t red[2][kScanThreads / 32];
 };
 
-__device__ __forceinline__ void scan_rare(float v, const float Lf[2], const float Uf[2], ScanShared &sh) {
-  if (!(fabsf(v) < __int_as_float(0x7F800000))) {
-    atomicAdd(&sh.nf, 1u);
-    if (v != v) atomicAdd(&sh.nan, 1u);
-    return;
-  }
-#pragma unroll
-  for (int br = 0; br < 2; ++br) {
-    if (v >= Lf[br] && v <= Uf[br]) {
-      if (v == Lf[br]) atomicAdd(&sh.eqL[br], 1u);
-      else if (v < Uf[br]) {
-        uint32_t pos = atomicAdd(&sh.cnt[br], 1u);
-        sh.cand[br][pos] = float_to_key(v);
-      } else atomicAdd(&sh.eqU[br], 1u);
-    }
-  }
-}
-
-// Common path, 11 predicated instructions, no branch: count "below" for both brackets and, when
-// the value is inside a bracket or non-finite (about 4% of pixels), push it on the thread's
-// private queue in shared memory (qaddr = shared-space byte address of the next free slot).
-// Queued values are classified exactly after the streaming loop.
-// NaN: every ordered compare is false; setp.gtu (unordered greater) is true -> queued.
+// Common path, 11 predicated instructions, no branch, no atomic: count "below" for both brackets
+// and, when the value is inside a bracket or non-finite (about 4% of pixels), store it in the
+// thread's private queue column in shared memory (qaddr = shared-space byte address of the next
+// free slot).  NaN: every ordered compare is false; setp.gtu (unordered greater) is true.
 __device__ __forceinline__ void scan_value(float v, const float Lf[2], const float Uf[2], uint32_t &b0,
                                            uint32_t &b1, uint32_t &qaddr) {
   asm volatile(
@@ -177,27 +157,29 @@ __device__ __forceinline__ void scan_value(float v, const float Lf[2], const flo
       : "memory");
 }
 
-template <bool NATIVE>
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_ok) {
-  extern __shared__ __align__(16) unsigned char scan_smem[];
-  ScanShared &sh = *reinterpret_cast<ScanShared *>(scan_smem);
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x;
-  FrameState *fs = kp.state + b;
-  const float *frame = kp.depth + (size_t)b * kp.g.D;
-  const uint32_t n = kp.g.P;
-  float Lf[2], Uf[2];
+__device__ __forceinline__ void bracket_floats(const FrameState *fs, float Lf[2], float Uf[2]) {
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
     const uint32_t L = fs->brL[br], U = fs->brU[br];
     Lf[br] = (L == 0u) ? -__int_as_float(0x7F800000) : key_to_float(L);           // open below
     Uf[br] = (U == 0xFFFFFFFFu) ? __int_as_float(0x7F800000) : key_to_float(U);   // open above
   }
-  if (tid < 2) { sh.cnt[tid] = 0; sh.eqL[tid] = 0; sh.eqU[tid] = 0; }
-  if (tid == 2) { sh.nf = 0; sh.nan = 0; }
+}
+
+template <bool NATIVE>
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_ok) {
+  __shared__ ScanShared sh;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  const uint32_t n = kp.g.P;
+  float Lf[2], Uf[2];
+  bracket_floats(fs, Lf, Uf);
+  if (tid < 2) sh.qtotal[tid] = 0;
   __syncthreads();
   uint32_t b0 = 0, b1 = 0;
-  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sh.queue[0][tid]);
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sh.pqueue[0][tid]);
   uint32_t qaddr = q0;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
 
@@ -244,12 +226,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
       }
     }
   }
-  // queued values (this thread's own slots: no barrier needed)
-  const uint32_t nq = (qaddr - q0) / (uint32_t)(kScanThreads * 4);
-  for (uint32_t j = 0; j < nq; ++j) scan_rare(sh.queue[j][tid], Lf, Uf, sh);
 
-  // CTA reduction of the two "below" counters; everything else already sits in shared memory
+  // epilogue: CTA totals -> 4 global atomics; deferred values -> the two brackets' raw queues
+  // (queue 0: v <= U0 or non-finite; queue 1: v >= L1; a value inside both goes to both)
   const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t nq = (qaddr - q0) / (uint32_t)(kScanThreads * 4);
+  uint32_t n0 = 0, n1 = 0;
+  for (uint32_t j = 0; j < nq; ++j) {
+    const float v = sh.pqueue[j][tid];
+    n0 += !(v > Uf[0]) ? 1u : 0u;   // also true for NaN
+    n1 += (v >= Lf[1]) ? 1u : 0u;   // +inf lands here too; harmless (it is in queue 0 as well)
+  }
+  const uint32_t pos0 = n0 ? atomicAdd(&sh.qtotal[0], n0) : 0u;
+  const uint32_t pos1 = n1 ? atomicAdd(&sh.qtotal[1], n1) : 0u;
   b0 = warp_sum(b0);
   b1 = warp_sum(b1);
   if (lane == 0) { sh.red[0][warp] = b0; sh.red[1][warp] = b1; }
@@ -258,22 +247,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
     uint32_t r = 0;
     for (int w = 0; w < kScanThreads / 32; ++w) r += sh.red[tid][w];
     if (r) atomicAdd(&fs->below[tid], r);
-    if (sh.eqL[tid]) atomicAdd(&fs->eqL[tid], sh.eqL[tid]);
-    if (sh.eqU[tid]) atomicAdd(&fs->eqU[tid], sh.eqU[tid]);
-    const uint32_t c = sh.cnt[tid];
-    sh.base[tid] = c ? atomicAdd(&fs->inside[tid], c) : 0u;
-  }
-  if (tid == 2) {
-    if (sh.nf) atomicAdd(&fs->n_nonfinite, sh.nf);
-    if (sh.nan) atomicAdd(&fs->n_nan, sh.nan);
+  } else if (tid < 4) {
+    const uint32_t t = sh.qtotal[tid - 2];
+    sh.gbase[tid - 2] = t ? atomicAdd(&fs->nqueue[tid - 2], t) : 0u;
   }
   __syncthreads();
-#pragma unroll
-  for (int br = 0; br < 2; ++br) {
-    const uint32_t c = sh.cnt[br], base = sh.base[br];
-    uint32_t *dst = kp.cand + ((size_t)b * 2 + br) * kp.cand_cap;
-    for (uint32_t i = tid; i < c; i += kScanThreads)
-      if (base + i < kp.cand_cap) dst[base + i] = sh.cand[br][i];
+  if (nq) {
+    float *gq0 = reinterpret_cast<float *>(kp.cand) + (size_t)b * 2 * kp.cand_cap;
+    float *gq1 = gq0 + kp.cand_cap;
+    uint32_t g0 = sh.gbase[0] + pos0, g1 = sh.gbase[1] + pos1;
+    for (uint32_t j = 0; j < nq; ++j) {
+      const float v = sh.pqueue[j][tid];
+      if (!(v > Uf[0])) { if (g0 < kp.cand_cap) gq0[g0] = v; ++g0; }
+      if (v >= Lf[1]) { if (g1 < kp.cand_cap) gq1[g1] = v; ++g1; }
+    }
   }
 }
 
@@ -309,17 +296,63 @@ __device__ void finalise_fast(FrameState *fs, uint32_t n) {
   vfs->status = D2PC_FRAME_READY;
 }
 
+// visit this thread's share of a raw queue, 8 independent loads in flight per thread
+template <typename F>
+__device__ __forceinline__ void for_each_queued(const float *q, uint32_t nq, F f) {
+  const uint32_t stride = blockDim.x;
+  uint32_t i = threadIdx.x;
+  for (; i + 7u * stride < nq; i += 8u * stride) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(q + i + (uint32_t)k * stride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f(v[k]);
+  }
+  for (; i < nq; i += stride) f(__ldg(q + i));
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
   extern __shared__ uint32_t s_hist[];  // 2 << kSelBits words
   __shared__ uint32_t s_res[2 * 2 + 40];
+  __shared__ uint32_t s_c[5];  // eqL, inside, eqU, non-finite, NaN
   const int br = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   FrameState *fs = kp.state + b;
   const uint32_t n = kp.g.P;
-  const uint32_t cap = kp.cand_cap;
-  const uint32_t *cand = kp.cand + ((size_t)b * 2 + br) * cap;
-  const uint32_t below = fs->below[br], eqL = fs->eqL[br], nin = fs->inside[br], eqU = fs->eqU[br];
+  const uint32_t qcap = kp.cand_cap;
+  const float *q = reinterpret_cast<const float *>(kp.cand) + ((size_t)b * 2 + br) * qcap;
+  const uint32_t nqueue = fs->nqueue[br];
+  const uint32_t nq = min(nqueue, qcap);
   const uint32_t L = fs->brL[br], U = fs->brU[br];
-  bool fail = (fs->n_nonfinite != 0u) || (fs->sample_ok == 0u) || (kp.force_fallback != 0);
+  float Lf2[2], Uf2[2];
+  bracket_floats(fs, Lf2, Uf2);
+  const float Lf = Lf2[br], Uf = Uf2[br];
+  if (tid < 5) s_c[tid] = 0;
+  __syncthreads();
+  {  // pass 0: classify the queued values against this bracket
+    uint32_t c_eqL = 0, c_in = 0, c_eqU = 0, c_nf = 0, c_nan = 0;
+    for_each_queued(q, nq, [&](float v) {
+      if (!(fabsf(v) < __int_as_float(0x7F800000))) { c_nf++; if (v != v) c_nan++; }
+      else if (v >= Lf && v <= Uf) {
+        if (v == Lf) c_eqL++;
+        else if (v < Uf) c_in++;
+        else c_eqU++;
+      }
+    });
+    c_eqL = warp_sum(c_eqL); c_in = warp_sum(c_in); c_eqU = warp_sum(c_eqU);
+    c_nf = warp_sum(c_nf); c_nan = warp_sum(c_nan);
+    if ((tid & 31) == 0) {
+      if (c_eqL) atomicAdd(&s_c[0], c_eqL);
+      if (c_in) atomicAdd(&s_c[1], c_in);
+      if (c_eqU) atomicAdd(&s_c[2], c_eqU);
+      if (c_nf) atomicAdd(&s_c[3], c_nf);
+      if (c_nan) atomicAdd(&s_c[4], c_nan);
+    }
+  }
+  __syncthreads();
+  const uint32_t below = fs->below[br], eqL = s_c[0], nin = s_c[1], eqU = s_c[2];
+  // a non-finite value anywhere in the frame shows up in queue 0; both CTAs must agree to fail,
+  // which the shared sel_fail flag takes care of
+  bool fail = (s_c[3] != 0u) || (nqueue > qcap) || (fs->sample_ok == 0u) || (kp.force_fallback != 0);
   RankPair rp = percentile_ranks(n, br ? D2PC_Q98 : D2PC_Q02);
   long long need[2] = {-1, -1};
   uint32_t key[2] = {0u, 0u};
@@ -335,17 +368,18 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
     fail = true;
   }
   const bool any_need = need[0] >= 0 || need[1] >= 0;
-  if (nin > cap && any_need) fail = true;
 
   if (!fail && any_need) {  // uniform over the CTA
-    // candidates are strictly inside (L, U) in float order; -0.0 == +0.0 there, so when a bound
-    // is a zero the other zero's key can sit one step outside the key interval: widen by one
+    // strictly inside (L, U) in float order; -0.0 == +0.0 there, so when a bound is a zero the
+    // other zero's key can sit one step outside the key interval: widen the key range by one
     const uint32_t lo0 = L > 0u ? L - 1u : 0u;
     const uint32_t hi0 = U < 0xFFFFFFFFu ? U + 1u : U;
     uint32_t rk[2], ok_[2];
     for (int t = 0; t < 2; ++t) rk[t] = (uint32_t)(need[t] >= 0 ? need[t] : need[1 - t]);
     const bool ok = block_hist_select<2, kSelBits>([&](auto f) {
-      for (uint32_t i = tid; i < nin; i += blockDim.x) f(__ldg(cand + i));
+      for_each_queued(q, nq, [&](float v) {
+        if (v > Lf && v < Uf) f(float_to_key(v));
+      });
     }, lo0, hi0, rk, ok_, s_hist, s_res);
     if (!ok) fail = true;
     for (int t = 0; t < 2; ++t)
@@ -355,6 +389,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
   if (tid == 0) {
     fs->sel_key[2 * br + 0] = key[0];
     fs->sel_key[2 * br + 1] = key[1];
+    fs->eqL[br] = eqL; fs->inside[br] = nin; fs->eqU[br] = eqU;
+    if (br == 0) { fs->n_nonfinite = s_c[3]; fs->n_nan = s_c[4]; }  // non-finite values live in queue 0
     if (fail) atomicOr(&fs->sel_fail, 1u);
     __threadfence();
     uint32_t ticket = atomicAdd(&fs->sel_done, 1u);
@@ -369,6 +405,39 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
 // fallback: exact 8-bit radix select over the whole map for flagged frames
 // ------------------------------------------------------------------------------------------
 enum { kStageMedian = 0, kStagePercentile = 1 };
+
+// The fallback does not trust anything the fast path counted: it recounts NaN / non-finite
+// values of the (virtually resized) map itself.
+__global__ void fb_reset_kernel(KParams kp) {
+  FrameState *fs = kp.state + blockIdx.x;
+  if (threadIdx.x == 0 && fs->status == D2PC_FRAME_NEEDS_FALLBACK) {
+    fs->n_nonfinite = 0; fs->n_nan = 0;
+    fs->min_key = 0xFFFFFFFFu; fs->max_key = 0u;
+  }
+}
+
+template <bool NATIVE>
+__global__ void __launch_bounds__(kScanThreads) fb_count_kernel(KParams kp) {
+  const int b = blockIdx.y, tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_NEEDS_FALLBACK) return;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  const uint32_t n = kp.g.P;
+  const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
+  uint32_t nf = 0, nan = 0;
+  for (int j = 0; j < kScanPerThread; ++j) {
+    uint32_t p = tile_base + (uint32_t)(j * kScanThreads + tid);
+    if (p >= n) break;
+    float v = depth_at<NATIVE>(frame, kp.g, p);
+    if (!is_finite_f32(v)) { nf++; if (is_nan_f32(v)) nan++; }
+  }
+  nf = warp_sum(nf);
+  nan = warp_sum(nan);
+  if ((tid & 31) == 0) {
+    if (nf) atomicAdd(&fs->n_nonfinite, nf);
+    if (nan) atomicAdd(&fs->n_nan, nan);
+  }
+}
 
 __global__ void fb_begin_kernel(KParams kp) {
   const int b = blockIdx.x;
@@ -548,7 +617,7 @@ __global__ void params_kernel(KParams kp, D2pcFrameParams *out) {
     o.lo32 = fs.norm.lo32; o.hi32 = fs.norm.hi32; o.den32 = fs.norm.den32; o.median = fs.norm.median;
     o.branch = fs.norm.branch; o.status = fs.status;
     o.n_nonfinite = fs.n_nonfinite; o.n_nan = fs.n_nan;
-    o.n_cand[0] = fs.inside[0]; o.n_cand[1] = fs.inside[1];
+    o.n_cand[0] = fs.nqueue[0]; o.n_cand[1] = fs.nqueue[1];
     o.reserved[0] = fs.sel_fail; o.reserved[1] = fs.sample_ok;
     out[b] = o;
   }
@@ -584,13 +653,7 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   }
   const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)d_depth & 15u) == 0u);
   dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
-  const size_t scan_smem_bytes = sizeof(ScanShared);
-  {
-    cudaError_t e = kp.g.native
-        ? cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes)
-        : cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes);
-    if (e != cudaSuccess) return record_cuda_error(e);
-  }
+  const size_t scan_smem_bytes = 0;
   if (kp.g.native) {
     sample_kernel<true><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
@@ -614,6 +677,11 @@ extern "C" int d2pc_stats_fallback_enqueue(const D2pcConfig *cfg, const float *d
   cudaStream_t st = (cudaStream_t)stream;
   KParams kp = make_kparams(*cfg, d_depth, d_workspace);
   dim3 grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
+  fb_reset_kernel<<<cfg->batch, 32, 0, st>>>(kp);
+  D2PC_CHECK_LAUNCH();
+  if (kp.g.native) fb_count_kernel<true><<<grid, kScanThreads, 0, st>>>(kp);
+  else fb_count_kernel<false><<<grid, kScanThreads, 0, st>>>(kp);
+  D2PC_CHECK_LAUNCH();
   fb_begin_kernel<<<cfg->batch, 256, 0, st>>>(kp);
   D2PC_CHECK_LAUNCH();
   for (int stage = 0; stage < 2; ++stage) {
