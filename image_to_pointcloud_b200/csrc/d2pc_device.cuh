@@ -86,8 +86,15 @@ struct __align__(256) FrameState {
   NormParams norm;
 };
 
+// One bilinear tap of the IPP model (d2pc_math.h axis_tap), 8 bytes, precomputed per call for
+// every destination column / row so the per-pixel kernels do no float64 coordinate math.
+struct __align__(8) TapEntry {
+  int32_t i0c;  // source index of tap 0; bit 31 set = clamped (output copies tap 0)
+  float t;      // float32 weight of tap 1
+};
+
 struct WsLayout {
-  size_t state_off, cand_off, tile_off, fbhist_off, total;
+  size_t state_off, cand_off, tile_off, fbhist_off, tap_off, total;
   uint32_t cand_cap;      // keys per (frame, bracket)
   uint32_t emit_tiles;    // emit CTAs per frame
 };
@@ -108,6 +115,7 @@ inline WsLayout make_layout(const D2pcConfig &c) {
   L.cand_off = off;   off = align_up(off + (size_t)c.batch * 2 * cap * sizeof(uint32_t), 256);
   L.tile_off = off;   off = align_up(off + (size_t)c.batch * L.emit_tiles * sizeof(unsigned long long), 256);
   L.fbhist_off = off; off = align_up(off + (size_t)c.batch * kFbTargets * 256 * sizeof(uint32_t), 256);
+  L.tap_off = off;    off = align_up(off + ((size_t)c.img_w + (size_t)c.img_h) * sizeof(TapEntry), 256);
   L.total = off;
   return L;
 }
@@ -121,6 +129,7 @@ struct KParams {
   uint32_t *cand;           // [batch][2][cand_cap] per-bracket raw queues of deferred values (float bits)
   unsigned long long *tile_state;  // [batch][emit_tiles]
   uint32_t *fb_hist;        // [batch][kFbTargets][256]
+  const TapEntry *xtab, *ytab;  // [W], [H] bilinear taps (resized depth only)
   uint32_t cand_cap, emit_tiles;
   int32_t force_fallback;
 };
@@ -136,6 +145,8 @@ inline KParams make_kparams(const D2pcConfig &c, const float *d_depth, void *ws)
   k.cand = (uint32_t *)(base + L.cand_off);
   k.tile_state = (unsigned long long *)(base + L.tile_off);
   k.fb_hist = (uint32_t *)(base + L.fbhist_off);
+  k.xtab = (const TapEntry *)(base + L.tap_off);
+  k.ytab = k.xtab + c.img_w;
   k.cand_cap = L.cand_cap;
   k.emit_tiles = L.emit_tiles;
   k.force_fallback = c.force_fallback;
@@ -319,18 +330,33 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32
   return x;
 }
 
+// a1 from the tap tables: same arithmetic as d2pc_math.h bilinear_sample (horizontal lerp on two
+// source rows, then vertical; clamped taps copy; corner blocks turn +-inf into NaN).
+__device__ __forceinline__ float bilinear_taps(const float *src, int32_t src_w, TapEntry tx, TapEntry ty) {
+  const int32_t x0 = tx.i0c & 0x7FFFFFFF, y0 = ty.i0c & 0x7FFFFFFF;
+  const bool cx = tx.i0c < 0, cy = ty.i0c < 0;
+  const float *row0 = src + (size_t)y0 * src_w;
+  const float a0 = __ldg(row0 + x0);
+  float r0 = a0;
+  if (!cx) r0 = fmaf(__ldg(row0 + x0 + 1) - a0, tx.t, a0);
+  if (cy) return (cx && is_inf_f32(r0)) ? nan_f32() : r0;
+  const float *row1 = row0 + src_w;
+  const float a1 = __ldg(row1 + x0);
+  float r1 = a1;
+  if (!cx) r1 = fmaf(__ldg(row1 + x0 + 1) - a1, tx.t, a1);
+  return fmaf(r1 - r0, ty.t, r0);
+}
+
 // Raw value of pixel p (row-major index into the H x W grid) of one frame's (virtually resized)
 // depth map.  NATIVE: the depth map already has the image size.
 template <bool NATIVE>
-__device__ __forceinline__ float depth_at(const float *frame, const Geom &g, uint32_t p) {
+__device__ __forceinline__ float depth_at(const float *frame, const KParams &kp, uint32_t p) {
   if (NATIVE) {
     return __ldg(frame + p);
   } else {
-    uint32_t v = p / (uint32_t)g.W;
-    uint32_t u = p - v * (uint32_t)g.W;
-    AxisTap tx = axis_tap((int32_t)u, g.scale_x, g.w);
-    AxisTap ty = axis_tap((int32_t)v, g.scale_y, g.h);
-    return bilinear_sample(frame, g.w, tx, ty);
+    const uint32_t v = p / (uint32_t)kp.g.W;
+    const uint32_t u = p - v * (uint32_t)kp.g.W;
+    return bilinear_taps(frame, kp.g.w, kp.xtab[u], kp.ytab[v]);
   }
 }
 #endif  // __CUDACC__

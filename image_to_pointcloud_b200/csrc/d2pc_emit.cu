@@ -80,127 +80,6 @@ __device__ __forceinline__ float byte_to_float(uint32_t w, uint32_t selector) {
 #define D2PC_B2 0x7442u
 #define D2PC_B3 0x7443u
 
-// Persistent CTAs (grid = resident CTAs), round-robin over the (frame, tile) list.  Each thread
-// owns 4 consecutive pixels of a tile; the 28 bytes it needs for its NEXT tile are requested
-// before it starts computing the current one (register double buffering), so HBM latency is
-// overlapped with the FP64 chain.  Staging smem is double buffered: one barrier per tile.
-struct FastArgs {
-  uint32_t tiles_per_frame, total_tiles;
-  unsigned long long magic_w;  // ceil(2^40 / W): p / W == (p * magic_w) >> 40 for p * W < 2^40
-  int32_t pc_simple;
-};
-
-struct FastRegs {
-  float4 d4;
-  uint32_t c0, c1, c2;
-};
-
-__device__ __forceinline__ void fast_prefetch(const KParams &kp, const EmitArgs &ea, const FastArgs &fa,
-                                              uint32_t t, int tid, FastRegs &r) {
-  const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
-  const uint32_t p0 = tile * (uint32_t)kEmitTile + 4u * (uint32_t)tid;
-  if (p0 < kp.g.P) {
-    r.d4 = ldg_stream_f4(kp.depth + (size_t)b * kp.g.P + p0);
-    const uint8_t *cp = ea.bgr + ((size_t)b * kp.g.P + p0) * 3;
-    r.c0 = ldg_stream_u32(cp); r.c1 = ldg_stream_u32(cp + 4); r.c2 = ldg_stream_u32(cp + 8);
-  }
-}
-
-// PREFETCH: persistent round-robin loop with register double buffering; otherwise one tile per CTA.
-template <bool PREFETCH, int MIN_BLOCKS>
-__global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KParams kp, EmitArgs ea, FastArgs fa) {
-  extern __shared__ __align__(16) float s_stage[];  // [2 buffers][xyz 3072 | rgb 3072]
-  const int tid = threadIdx.x;
-  const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
-  uint32_t t = blockIdx.x;
-  if (t >= fa.total_tiles) return;
-  FastRegs cur, nxt;
-  fast_prefetch(kp, ea, fa, t, tid, cur);
-  int buf = 0;
-  while (t < fa.total_tiles) {
-    const uint32_t tn = PREFETCH ? t + gridDim.x : fa.total_tiles;
-    if (PREFETCH && tn < fa.total_tiles) fast_prefetch(kp, ea, fa, tn, tid, nxt);
-    const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
-    const FrameState *fs = kp.state + b;
-    const uint32_t tile_base = tile * (uint32_t)kEmitTile;
-    const uint32_t p0 = tile_base + 4u * (uint32_t)tid;
-    float *s_xyz = s_stage + buf * (2 * kEmitTile * 3);
-    float *s_rgb = s_xyz + kEmitTile * 3;
-    const bool ready = fs->status == D2PC_FRAME_READY;  // uniform per CTA
-    if (ready && p0 < P) {
-      const NormParams np_ = fs->norm;
-      const uint32_t v = (uint32_t)(((unsigned long long)p0 * fa.magic_w) >> 40), u = p0 - v * W;
-      const float raw[4] = {cur.d4.x, cur.d4.y, cur.d4.z, cur.d4.w};
-      float o[12];
-      if (np_.simple && fa.pc_simple) {  // uniform per frame
-        const double ux0 = (double)(int32_t)u - ea.pc.cx;
-        const double vy = (double)(int32_t)v - ea.pc.cy;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          simple_point(raw[k], ux0 + (double)k, vy, np_, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double n = normalised_depth(raw[k], np_, ea.pc.invert);
-          back_project(n, (int32_t)u + k, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
-        }
-      }
-      float *sx = s_xyz + 12 * tid;
-      stage_f4(sx, o[0], o[1], o[2], o[3]);
-      stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
-      stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
-      // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
-      const uint32_t c0 = cur.c0, c1 = cur.c1, c2 = cur.c2;
-      float *sr = s_rgb + 12 * tid;
-      stage_f4(sr, byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
-               byte_to_float(c1, D2PC_B1));
-      stage_f4(sr + 4, byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3), byte_to_float(c2, D2PC_B0),
-               byte_to_float(c1, D2PC_B3));
-      stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
-               byte_to_float(c2, D2PC_B1));
-    }
-    __syncthreads();
-    if (ready) {
-      const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
-      const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
-      const uint32_t nvec = rows * 3u / 4u;  // rows % 4 == 0 here
-      for (uint32_t i = tid; i < nvec; i += kEmitThreads) {
-        stg_stream_f4(ea.xyz + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_xyz + 4 * i));
-        stg_stream_f4(ea.rgb + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_rgb + 4 * i));
-      }
-      if (tile == 0 && tid == 0) ea.count[b] = kp.g.N;
-    }
-    buf ^= 1;
-    t = tn;
-    if (PREFETCH) cur = nxt;
-  }
-}
-
-template <bool PREFETCH, int MIN_BLOCKS>
-static int launch_emit_fast(const KParams &kp, const EmitArgs &ea, const FastArgs &fa, cudaStream_t st) {
-  const size_t smem = (PREFETCH ? 2 : 1) * 2 * (size_t)kEmitTile * 3 * sizeof(float);  // 48 / 24 KB
-  cudaError_t e = cudaFuncSetAttribute(emit_fast_kernel<PREFETCH, MIN_BLOCKS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return record_cuda_error(e);
-  uint32_t ctas = fa.total_tiles;
-  if (PREFETCH) {
-    int dev = 0, sms = 148, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_fast_kernel<PREFETCH, MIN_BLOCKS>,
-                                                      kEmitThreads, smem);
-    if (e != cudaSuccess) return record_cuda_error(e);
-    if (per_sm < 1) per_sm = 1;
-    ctas = (uint32_t)sms * (uint32_t)per_sm;  // persistent: exactly one resident wave
-    if (ctas > fa.total_tiles) ctas = fa.total_tiles;
-  }
-  emit_fast_kernel<PREFETCH, MIN_BLOCKS><<<ctas, kEmitThreads, smem, st>>>(kp, ea, fa);
-  return D2PC_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// generic path
-// ------------------------------------------------------------------------------------------
 // tile_state word: (flag << 32) | value ; flag 0 = not ready, 1 = tile aggregate, 2 = inclusive
 __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long long *ts, int tile) {
   const int lane = threadIdx.x & 31;
@@ -223,6 +102,171 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
   return exclusive;
 }
 
+// One tile of 1024 consecutive pixels per CTA, 4 consecutive pixels per thread (W % 4 == 0, so
+// they share a row).  NATIVE: one 16 B depth load; otherwise 4 table-driven bilinear samples of
+// the (L2-resident) low-resolution map.  MASK: depth-range / non-finite mask with ordered
+// compaction (CTA scan + decoupled look-back over the frame's tiles, tiles dispatched in order).
+// High occupancy matters more than per-thread ILP here (measured: 6 CTAs/SM beat 3-5 and beat a
+// persistent register-prefetching variant), hence MIN_BLOCKS.
+struct FastArgs {
+  uint32_t tiles_per_frame, total_tiles;
+  unsigned long long magic_w;  // ceil(2^40 / W): p / W == (p * magic_w) >> 40 for p * W < 2^40
+  int32_t pc_simple;
+};
+
+template <bool NATIVE, bool MASK, bool BOUNDS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KParams kp, EmitArgs ea, FastArgs fa) {
+  extern __shared__ __align__(16) float s_stage[];  // xyz [3072 + 4] | rgb [3072 + 4]
+  __shared__ uint32_t s_warp[kEmitThreads / 32];
+  __shared__ uint32_t s_prefix;
+  __shared__ uint32_t s_b[6][kEmitThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
+  const uint32_t t = blockIdx.x;
+  const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
+  FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_READY) return;  // uniform per CTA (and per frame: no tile of it publishes)
+  const uint32_t tile_base = tile * (uint32_t)kEmitTile;
+  const uint32_t p0 = tile_base + 4u * (uint32_t)tid;
+  float *s_xyz = s_stage;
+  float *s_rgb = s_stage + (kEmitTile * 3 + 4);
+  float o[12];
+  uint32_t c0 = 0, c1 = 0, c2 = 0;
+  bool keep[4] = {false, false, false, false};
+  uint32_t my_cnt = 0;
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  if (p0 < P) {
+    const uint32_t v = (uint32_t)(((unsigned long long)p0 * fa.magic_w) >> 40), u = p0 - v * W;
+    float raw[4];
+    if (NATIVE) {
+      const float4 d4 = ldg_stream_f4(kp.depth + (size_t)b * P + p0);
+      raw[0] = d4.x; raw[1] = d4.y; raw[2] = d4.z; raw[3] = d4.w;
+    } else {
+      const float *frame = kp.depth + (size_t)b * kp.g.D;
+      const TapEntry ty = kp.ytab[v];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) raw[k] = bilinear_taps(frame, kp.g.w, kp.xtab[u + k], ty);
+    }
+    const uint8_t *cp = ea.bgr + ((size_t)b * P + p0) * 3;
+    c0 = ldg_stream_u32(cp); c1 = ldg_stream_u32(cp + 4); c2 = ldg_stream_u32(cp + 8);
+    const NormParams np_ = fs->norm;
+    if (np_.simple && fa.pc_simple) {  // uniform per frame
+      const double ux0 = (double)(int32_t)u - ea.pc.cx;
+      const double vy = (double)(int32_t)v - ea.pc.cy;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        simple_point(raw[k], ux0 + (double)k, vy, np_, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double n = normalised_depth(raw[k], np_, ea.pc.invert);
+        back_project(n, (int32_t)u + k, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bool kk = true;
+      if (MASK) {
+        const float z = o[3 * k + 2];
+        if (ea.use_z) kk = (z >= ea.z_min) && (z <= ea.z_max);
+        if (ea.drop_nf && !is_finite_f32(raw[k])) kk = false;
+      }
+      keep[k] = kk;
+      my_cnt += kk ? 1u : 0u;
+      if (BOUNDS && kk) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t key = float_to_key(o[3 * k + c]);
+          mn[c] = min(mn[c], key); mx[c] = max(mx[c], key);
+        }
+      }
+    }
+  }
+  if (!MASK) {
+    if (p0 < P) {
+      float *sx = s_xyz + 12 * tid, *sr = s_rgb + 12 * tid;
+      stage_f4(sx, o[0], o[1], o[2], o[3]);
+      stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
+      stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
+      // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
+      stage_f4(sr, byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
+               byte_to_float(c1, D2PC_B1));
+      stage_f4(sr + 4, byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3), byte_to_float(c2, D2PC_B0),
+               byte_to_float(c1, D2PC_B3));
+      stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
+               byte_to_float(c2, D2PC_B1));
+    }
+    __syncthreads();
+    const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
+    const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
+    const uint32_t nvec = rows * 3u / 4u;  // rows % 4 == 0 here
+    for (uint32_t i = tid; i < nvec; i += kEmitThreads) {
+      stg_stream_f4(ea.xyz + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_xyz + 4 * i));
+      stg_stream_f4(ea.rgb + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_rgb + 4 * i));
+    }
+    if (tile == 0 && tid == 0) ea.count[b] = kp.g.N;
+  } else {
+    // CTA exclusive scan of the per-thread keep counts
+    uint32_t incl = my_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEmitThreads / 32; ++w) {
+      uint32_t c = s_warp[w];
+      if (w < warp) warp_off += c;
+      total += c;
+    }
+    uint32_t local = warp_off + incl - my_cnt;
+    volatile unsigned long long *ts = kp.tile_state + (size_t)b * kp.emit_tiles;
+    if (warp == 0) {
+      if (lane == 0 && tile > 0) ts[tile] = (1ull << 32) | (unsigned long long)total;
+      uint32_t ex = (tile == 0) ? 0u : lookback_exclusive(ts, (int)tile);
+      if (lane == 0) {
+        ts[tile] = (2ull << 32) | (unsigned long long)(ex + total);
+        s_prefix = ex;
+        if (tile == kp.emit_tiles - 1) ea.count[b] = ex + total;
+      }
+    }
+    __syncthreads();
+    const size_t g0 = ((size_t)b * kp.g.N + s_prefix) * 3;
+    const uint32_t s_off = (uint32_t)(g0 & 3);
+    const float col[12] = {
+        byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
+        byte_to_float(c1, D2PC_B1), byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3),
+        byte_to_float(c2, D2PC_B0), byte_to_float(c1, D2PC_B3), byte_to_float(c1, D2PC_B2),
+        byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2), byte_to_float(c2, D2PC_B1)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!keep[k]) continue;
+      const uint32_t w = s_off + 3u * local;
+      s_xyz[w] = o[3 * k]; s_xyz[w + 1] = o[3 * k + 1]; s_xyz[w + 2] = o[3 * k + 2];
+      s_rgb[w] = col[3 * k]; s_rgb[w + 1] = col[3 * k + 1]; s_rgb[w + 2] = col[3 * k + 2];
+      local++;
+    }
+    __syncthreads();
+    copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0);
+    copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0);
+  }
+  if (BOUNDS) reduce_bounds(fs, mn, mx, s_b);
+}
+
+template <bool NATIVE, bool MASK, int MIN_BLOCKS>
+static int launch_emit_fast(const KParams &kp, const EmitArgs &ea, const FastArgs &fa, cudaStream_t st) {
+  const size_t smem = 2 * ((size_t)kEmitTile * 3 + 4) * sizeof(float);
+  if (ea.want_bounds) emit_fast_kernel<NATIVE, MASK, true, 5><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
+  else emit_fast_kernel<NATIVE, MASK, false, MIN_BLOCKS><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
+  return D2PC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path (any stride, BGRA / grey images, widths that are not a multiple of 4)
+// ------------------------------------------------------------------------------------------
 template <bool NATIVE, bool MASK>
 __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, EmitArgs ea) {
   __shared__ __align__(16) float s_xyz[kEmitTile * 3 + 4];
@@ -251,7 +295,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
     const uint32_t jv = i / (uint32_t)g.nu, ju = i - jv * (uint32_t)g.nu;
     const uint32_t u = ju * (uint32_t)g.step, v = jv * (uint32_t)g.step;
     const uint32_t p = v * (uint32_t)g.W + u;
-    const float raw = depth_at<NATIVE>(frame, g, p);
+    const float raw = depth_at<NATIVE>(frame, kp, p);
     const double n = normalised_depth(raw, np_, ea.pc.invert);
     back_project(n, (int32_t)u, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
     if (g.C >= 3) {
@@ -387,8 +431,8 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     D2PC_CHECK_LAUNCH();
   }
   dim3 grid(kp.emit_tiles, cfg->batch);
-  const bool fast = !mask && !cfg->want_bounds && kp.g.native && cfg->step == 1 && cfg->img_c == 3 &&
-                    (cfg->img_w & 3) == 0 && (((uintptr_t)d_depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) &&
+  const bool fast = cfg->step == 1 && cfg->img_c == 3 && (cfg->img_w & 3) == 0 &&
+                    (((uintptr_t)d_depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) &&
                     ((unsigned long long)kp.g.P * (unsigned long long)cfg->img_w < (1ull << 40));
   if (fast) {
     FastArgs fa;
@@ -396,21 +440,9 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     fa.total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
     fa.magic_w = ((1ull << 40) + (unsigned long long)cfg->img_w - 1ull) / (unsigned long long)cfg->img_w;
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
-    static int variant = -1;  // tuning knob (D2PC_EMIT_VARIANT), default chosen from measurements
-    if (variant < 0) {
-      const char *v = getenv("D2PC_EMIT_VARIANT");
-      variant = v ? atoi(v) : 5;
-    }
     int rcl;
-    switch (variant) {
-      case 0: rcl = launch_emit_fast<true, 3>(kp, ea, fa, st); break;
-      case 1: rcl = launch_emit_fast<true, 4>(kp, ea, fa, st); break;
-      case 3: rcl = launch_emit_fast<false, 5>(kp, ea, fa, st); break;
-      case 4: rcl = launch_emit_fast<false, 3>(kp, ea, fa, st); break;
-      case 6: rcl = launch_emit_fast<false, 8>(kp, ea, fa, st); break;
-      case 2: rcl = launch_emit_fast<false, 4>(kp, ea, fa, st); break;
-      default: rcl = launch_emit_fast<false, 6>(kp, ea, fa, st); break;
-    }
+    if (kp.g.native) rcl = mask ? launch_emit_fast<true, true, 5>(kp, ea, fa, st) : launch_emit_fast<true, false, 6>(kp, ea, fa, st);
+    else rcl = mask ? launch_emit_fast<false, true, 5>(kp, ea, fa, st) : launch_emit_fast<false, false, 5>(kp, ea, fa, st);
     if (rcl) return rcl;
   } else if (kp.g.native) {
     if (mask) emit_generic_kernel<true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);

@@ -28,6 +28,23 @@ __device__ __forceinline__ int32_t bracket_margin(double q, int S) {
 }
 
 // ------------------------------------------------------------------------------------------
+// taps_kernel: a1 coordinate math once per call (float64, exactly d2pc_math.h axis_tap)
+// ------------------------------------------------------------------------------------------
+__global__ void taps_kernel(KParams kp) {
+  TapEntry *xt = const_cast<TapEntry *>(kp.xtab), *yt = const_cast<TapEntry *>(kp.ytab);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kp.g.W) {
+    AxisTap a = axis_tap(i, kp.g.scale_x, kp.g.w);
+    xt[i].i0c = a.i0 | (a.clamped ? (int32_t)0x80000000 : 0);
+    xt[i].t = a.t;
+  } else if (i < kp.g.W + kp.g.H) {
+    AxisTap a = axis_tap(i - kp.g.W, kp.g.scale_y, kp.g.h);
+    yt[i - kp.g.W].i0c = a.i0 | (a.clamped ? (int32_t)0x80000000 : 0);
+    yt[i - kp.g.W].t = a.t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // sample_kernel
 // ------------------------------------------------------------------------------------------
 template <bool NATIVE>
@@ -74,7 +91,7 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     uint32_t start = (uint32_t)(((unsigned long long)j * n) / S);
     uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * n) / S);
     uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)b * 0x85EBCA6Bu + 12345u) % (end - start);
-    float v = depth_at<NATIVE>(frame, kp.g, idx);
+    float v = depth_at<NATIVE>(frame, kp, idx);
     k[e] = 0xFFFFFFFFu;
     if (is_finite_f32(v)) k[e] = float_to_key(v); else bad = true;
   }
@@ -207,21 +224,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
     }
   } else {
     const uint32_t W = (uint32_t)kp.g.W;
-#pragma unroll 1
+#pragma unroll 2
     for (int j = 0; j < kScanPerThread / 4; ++j) {
       uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
       if (p >= n) continue;
       uint32_t v = p / W;
       uint32_t u = p - v * W;
-      AxisTap ty = axis_tap((int32_t)v, kp.g.scale_y, kp.g.h);
+      TapEntry ty = kp.ytab[v];
       for (uint32_t k = 0; k < 4u && p + k < n; ++k) {
         if (u >= W) {
           u -= W;
           v += 1;
-          ty = axis_tap((int32_t)v, kp.g.scale_y, kp.g.h);
+          ty = kp.ytab[v];
         }
-        AxisTap tx = axis_tap((int32_t)u, kp.g.scale_x, kp.g.w);
-        scan_value(bilinear_sample(frame, kp.g.w, tx, ty), Lf, Uf, b0, b1, qaddr);
+        scan_value(bilinear_taps(frame, kp.g.w, kp.xtab[u], ty), Lf, Uf, b0, b1, qaddr);
         u += 1;
       }
     }
@@ -428,7 +444,7 @@ __global__ void __launch_bounds__(kScanThreads) fb_count_kernel(KParams kp) {
   for (int j = 0; j < kScanPerThread; ++j) {
     uint32_t p = tile_base + (uint32_t)(j * kScanThreads + tid);
     if (p >= n) break;
-    float v = depth_at<NATIVE>(frame, kp.g, p);
+    float v = depth_at<NATIVE>(frame, kp, p);
     if (!is_finite_f32(v)) { nf++; if (is_nan_f32(v)) nan++; }
   }
   nf = warp_sum(nf);
@@ -483,7 +499,7 @@ __global__ void __launch_bounds__(kScanThreads) fb_hist_kernel(KParams kp, int s
   for (int j = 0; j < kScanPerThread; ++j) {
     uint32_t p = tile_base + (uint32_t)(j * kScanThreads + tid);
     if (p >= n) break;
-    float v = depth_at<NATIVE>(frame, kp.g, p);
+    float v = depth_at<NATIVE>(frame, kp, p);
     if (stage == kStageMedian) {
       if (is_nan_f32(v)) continue;
     } else {
@@ -654,6 +670,10 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)d_depth & 15u) == 0u);
   dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
   const size_t scan_smem_bytes = 0;
+  if (!kp.g.native) {
+    taps_kernel<<<(kp.g.W + kp.g.H + 255) / 256, 256, 0, st>>>(kp);
+    D2PC_CHECK_LAUNCH();
+  }
   if (kp.g.native) {
     sample_kernel<true><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
