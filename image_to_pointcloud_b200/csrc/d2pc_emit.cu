@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 // High occupancy matters more than per-thread ILP here (measured: 6 CTAs/SM beat 3-5 and beat a
 // persistent register-prefetching variant), hence MIN_BLOCKS.
 struct FastArgs {
-  uint32_t tiles_per_frame, total_tiles;
+  uint32_t tiles_per_frame, total_tiles, batch;
   unsigned long long magic_w;  // ceil(2^40 / W): p / W == (p * magic_w) >> 40 for p * W < 2^40
   int32_t pc_simple;
 };
@@ -123,7 +123,11 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
   const uint32_t t = blockIdx.x;
-  const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
+  // MASK: consecutive CTAs work on different frames (tile-major order), so a frame has only
+  // in-flight/batch tiles in flight and the look-back finds an inclusive prefix within a round
+  // or two; a tile's predecessors (same frame, lower tile) still have lower CTA indices.
+  const uint32_t b = MASK ? t % fa.batch : t / fa.tiles_per_frame;
+  const uint32_t tile = MASK ? t / fa.batch : t - b * fa.tiles_per_frame;
   FrameState *fs = kp.state + b;
   if (fs->status != D2PC_FRAME_READY) return;  // uniform per CTA (and per frame: no tile of it publishes)
   const uint32_t tile_base = tile * (uint32_t)kEmitTile;
@@ -438,11 +442,12 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     FastArgs fa;
     fa.tiles_per_frame = kp.emit_tiles;
     fa.total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
+    fa.batch = (uint32_t)cfg->batch;
     fa.magic_w = ((1ull << 40) + (unsigned long long)cfg->img_w - 1ull) / (unsigned long long)cfg->img_w;
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
     int rcl;
     if (kp.g.native) rcl = mask ? launch_emit_fast<true, true, 5>(kp, ea, fa, st) : launch_emit_fast<true, false, 6>(kp, ea, fa, st);
-    else rcl = mask ? launch_emit_fast<false, true, 5>(kp, ea, fa, st) : launch_emit_fast<false, false, 5>(kp, ea, fa, st);
+    else rcl = mask ? launch_emit_fast<false, true, 5>(kp, ea, fa, st) : launch_emit_fast<false, false, 6>(kp, ea, fa, st);
     if (rcl) return rcl;
   } else if (kp.g.native) {
     if (mask) emit_generic_kernel<true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);

@@ -1,0 +1,47 @@
+"""Runs one workload variant a few times (for ncu captures): python profiles/run_variant.py NAME [iters]
+NAME: native | dav2 | mask | mask4k | native4k | medium_dav2"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import image_to_pointcloud_b200 as m  # noqa: E402
+
+VARIANTS = {
+    "native": (1080, 1920, 1080, 1920, 16, None, "high"),
+    "dav2": (1080, 1920, 518, 924, 16, None, "high"),
+    "mask": (1080, 1920, 1080, 1920, 16, (0.5, 9.5), "high"),
+    "mask4k": (2160, 3840, 2160, 3840, 8, (0.5, 9.5), "high"),
+    "native4k": (2160, 3840, 2160, 3840, 8, None, "high"),
+    "medium_dav2": (1080, 1920, 518, 924, 16, None, "medium"),
+}
+
+
+def main():
+    name = sys.argv[1]
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    H, W, h, w, B, zr, dens = VARIANTS[name]
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    eng = m.FrameEngine(H, W, h, w, batch=B, device=dev)
+    cfg = eng.make_config(density=dens, z_range=zr)
+    depth = torch.rand((B, h, w), generator=g, device=dev) * 20
+    bgr = torch.randint(0, 256, (B, H, W, 3), generator=g, device=dev, dtype=torch.uint8)
+    xyz, rgb = eng.alloc_outputs(cfg)
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(iters + 2):
+        if i == 2:
+            a.record()
+        eng.enqueue_stats(cfg, depth, s)
+        eng.enqueue_emit(cfg, depth, bgr, xyz, rgb, cnt, None, s)
+    b.record()
+    torch.cuda.synchronize()
+    print(name, "ms/iter", a.elapsed_time(b) / iters, "kept", int(cnt.sum()), "of", B * eng.points_per_frame(cfg))
+
+
+if __name__ == "__main__":
+    main()
