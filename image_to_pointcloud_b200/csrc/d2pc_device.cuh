@@ -18,7 +18,7 @@ constexpr int kSample2Size = 4096;     // level-2 sample over a bracket's candid
 constexpr int kSortCap = 16384;        // frames with at most this many pixels skip sampling
 constexpr int kSelBits = 12;           // bucket histogram levels of the exact selection: 4096 bins
 constexpr int kScanThreads = 256;
-constexpr int kScanPerThread = 16;
+constexpr int kScanPerThread = 32;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // 4096 pixels per CTA
 constexpr int kSelThreads = 1024;
 constexpr int kEmitThreads = 256;

@@ -201,23 +201,35 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
   const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
 
   if (NATIVE) {
-    float4 r[kScanPerThread / 4];
-    bool full[kScanPerThread / 4];
+    if (vec_ok && tile_base + (uint32_t)kScanTile <= n) {
+      // full tile: groups of 16 pixels per thread; the next group's four 16 B loads are issued
+      // before the current group is compared.  The rolled loop keeps ptxas from hoisting all 160
+      // compares ahead of their uses (which spills predicates into bit-masks).
+      constexpr int NG = kScanPerThread / 16;
+      const float *src = frame + tile_base + 4u * (uint32_t)tid;
+      float4 r[4], nx[4];
 #pragma unroll
-    for (int j = 0; j < kScanPerThread / 4; ++j) {
-      uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
-      full[j] = vec_ok && (p + 3u < n);
-      if (full[j]) r[j] = ldg_stream_f4(frame + p);
-    }
+      for (int j = 0; j < 4; ++j) r[j] = ldg_stream_f4(src + (size_t)j * (4 * kScanThreads));
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        if (g + 1 < NG) {
 #pragma unroll
-    for (int j = 0; j < kScanPerThread / 4; ++j) {
-      uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
-      if (full[j]) {
-        scan_value(r[j].x, Lf, Uf, b0, b1, qaddr);
-        scan_value(r[j].y, Lf, Uf, b0, b1, qaddr);
-        scan_value(r[j].z, Lf, Uf, b0, b1, qaddr);
-        scan_value(r[j].w, Lf, Uf, b0, b1, qaddr);
-      } else {
+          for (int j = 0; j < 4; ++j) nx[j] = ldg_stream_f4(src + (size_t)((g + 1) * 4 + j) * (4 * kScanThreads));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          scan_value(r[j].x, Lf, Uf, b0, b1, qaddr);
+          scan_value(r[j].y, Lf, Uf, b0, b1, qaddr);
+          scan_value(r[j].z, Lf, Uf, b0, b1, qaddr);
+          scan_value(r[j].w, Lf, Uf, b0, b1, qaddr);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = nx[j];
+      }
+    } else {  // last tile of a frame / unaligned frames
+#pragma unroll 1
+      for (int j = 0; j < kScanPerThread / 4; ++j) {
+        const uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
         for (uint32_t k = 0; k < 4u; ++k)
           if (p + k < n) scan_value(__ldg(frame + p + k), Lf, Uf, b0, b1, qaddr);
       }
@@ -327,7 +339,7 @@ __device__ __forceinline__ void for_each_queued(const float *q, uint32_t nq, F f
   for (; i < nq; i += stride) f(__ldg(q + i));
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(KParams kp) {
+__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(KParams kp) {
   extern __shared__ uint32_t s_hist[];  // 2 << kSelBits words
   __shared__ uint32_t s_res[2 * 2 + 40];
   __shared__ uint32_t s_c[5];  // eqL, inside, eqU, non-finite, NaN
