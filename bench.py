@@ -43,8 +43,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step (default: batch)")
+    ap.add_argument("--batch", type=int, default=128, help="frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=32, help="frames per e2e step (0: same as --batch)")
     ap.add_argument("--chunk", type=int, default=8, help="frames per pipeline chunk in the e2e path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time mask / resized / 4K variants")
@@ -105,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -124,6 +124,17 @@ class ClockSampler:
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def measured_traffic_per_frame():
+    """dram__bytes_read.sum + dram__bytes_write.sum of emit_fast_kernel per 1080p frame, from the
+    committed `ncu --set full` capture (profiles/r01_emit_traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_emit_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_frame"])
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -354,7 +365,8 @@ def run_ours(args):
                     "api": "HostFramePipeline.run_pinned (pinned host in/out, 3 streams, chunk=%d)" % pipe.chunk},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "kernel": "emit_fast_kernel", "achieved": round(achieved, 1),
-                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": (round(measured_traffic_per_frame() * B) if measured_traffic_per_frame() else None),
                          "peak_source": peak_src, "alg_bytes_per_launch": emit_bytes,
                          "launch_ms": round(emit_ms, 4),
                          "whole_path_gbs_per_gpu": round(path_gbs, 1),

@@ -79,7 +79,9 @@ struct __align__(256) FrameState {
   uint32_t fb_rank[kFbTargets];
   uint32_t fb_active;     // number of live targets in the current stage
   uint32_t fb_any_nan;    // repaired map still holds NaN (median itself NaN)
-  // emit
+  // emit: depth-space mask of the frame (ax-1): mode 0 = exact z compare, 1 = [mask_lo, mask_hi] on raw depth
+  int32_t mask_mode;
+  float mask_lo, mask_hi;
   uint32_t emit_count;
   uint32_t bounds_min[3], bounds_max[3];  // ordered keys of kept x, y, z
   // parameters consumed by emit
@@ -94,7 +96,7 @@ struct __align__(8) TapEntry {
 };
 
 struct WsLayout {
-  size_t state_off, cand_off, tile_off, fbhist_off, tap_off, total;
+  size_t state_off, cand_off, tile_off, fbhist_off, tap_off, resized_off, total;
   uint32_t cand_cap;      // keys per (frame, bracket)
   uint32_t emit_tiles;    // emit CTAs per frame
 };
@@ -116,6 +118,9 @@ inline WsLayout make_layout(const D2pcConfig &c) {
   L.tile_off = off;   off = align_up(off + (size_t)c.batch * L.emit_tiles * sizeof(unsigned long long), 256);
   L.fbhist_off = off; off = align_up(off + (size_t)c.batch * kFbTargets * 256 * sizeof(uint32_t), 256);
   L.tap_off = off;    off = align_up(off + ((size_t)c.img_w + (size_t)c.img_h) * sizeof(TapEntry), 256);
+  // resized depth only: the scan materialises the (H x W) map once; every later kernel reads it
+  L.resized_off = off;
+  if (!g.native) off = align_up(off + (size_t)c.batch * g.P * sizeof(float), 256);
   L.total = off;
   return L;
 }
@@ -130,6 +135,7 @@ struct KParams {
   unsigned long long *tile_state;  // [batch][emit_tiles]
   uint32_t *fb_hist;        // [batch][kFbTargets][256]
   const TapEntry *xtab, *ytab;  // [W], [H] bilinear taps (resized depth only)
+  float *resized;           // [batch][P] materialised resized map (resized depth only), else nullptr
   uint32_t cand_cap, emit_tiles;
   int32_t force_fallback;
 };
@@ -147,10 +153,25 @@ inline KParams make_kparams(const D2pcConfig &c, const float *d_depth, void *ws)
   k.fb_hist = (uint32_t *)(base + L.fbhist_off);
   k.xtab = (const TapEntry *)(base + L.tap_off);
   k.ytab = k.xtab + c.img_w;
+  k.resized = k.g.native ? nullptr : (float *)(base + L.resized_off);
   k.cand_cap = L.cand_cap;
   k.emit_tiles = L.emit_tiles;
   k.force_fallback = c.force_fallback;
   return k;
+}
+
+// View of the per-pixel (H x W) depth map for the kernels that run after the scan: the input itself
+// when it already has the image size, otherwise the map the scan materialised.
+inline KParams per_pixel_view(const KParams &kp) {
+  KParams v = kp;
+  if (!kp.g.native) {
+    v.depth = kp.resized;
+    v.g.D = kp.g.P;
+    v.g.h = kp.g.H;
+    v.g.w = kp.g.W;
+    v.g.native = 1;
+  }
+  return v;
 }
 
 int validate_config(const D2pcConfig *cfg);   // d2pc_api.cu

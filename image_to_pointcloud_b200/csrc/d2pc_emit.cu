@@ -102,6 +102,112 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
   return exclusive;
 }
 
+// ax-1 predicate.  Frames whose z is provably monotone in the raw depth (mask_mode 1) compare the
+// raw value against the frame's depth-space interval; all other frames compare the emitted z.
+__device__ __forceinline__ bool mask_keep(float raw, float z32, const FrameState *fs, const EmitArgs &ea) {
+  bool kk = true;
+  if (ea.use_z) {
+    if (fs->mask_mode == 1) kk = (raw >= fs->mask_lo) && (raw <= fs->mask_hi);
+    else kk = (z32 >= ea.z_min) && (z32 <= ea.z_max);
+  }
+  if (ea.drop_nf && !is_finite_f32(raw)) kk = false;
+  return kk;
+}
+
+__global__ void mask_prepare_kernel(KParams kp, EmitArgs ea, int pc_simple) {
+  FrameState *fs = kp.state + blockIdx.x;
+  if (threadIdx.x != 0 || fs->status != D2PC_FRAME_READY) return;
+  fs->mask_mode = 0;
+  if (ea.use_z && fs->norm.simple && pc_simple) {
+    float lo, hi;
+    mask_interval(fs->norm, ea.pc, ea.z_min, ea.z_max, &lo, &hi);
+    fs->mask_lo = lo;
+    fs->mask_hi = hi;
+    fs->mask_mode = 1;
+  }
+}
+
+// kept points per emit tile (same tiling and predicate as emit_fast_kernel<MASK>): reads the
+// per-pixel depth map only (4 B/px).  One warp per 1024-pixel tile: 8 independent 16 B loads per
+// lane, a warp reduction, no shared memory, no barrier.  Mode-0 frames evaluate the exact chain.
+constexpr int kCountWarps = 8;
+__global__ void __launch_bounds__(kCountWarps * 32) mask_count_kernel(KParams kp, EmitArgs ea, uint32_t tiles_per_frame,
+                                                                     uint32_t total_tiles) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * (uint32_t)kCountWarps + (uint32_t)warp;
+  if (t >= total_tiles) return;
+  const uint32_t b = t / tiles_per_frame, tile = t - b * tiles_per_frame;
+  const FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_READY) return;
+  const uint32_t P = kp.g.P;
+  const uint32_t tile_base = tile * (uint32_t)kEmitTile;
+  const float *src = kp.depth + (size_t)b * P + tile_base;
+  float4 r[8];
+  bool ok[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t q = 4u * (uint32_t)(j * 32 + lane);
+    ok[j] = tile_base + q < P;  // P % 4 == 0 on this path
+    if (ok[j]) r[j] = ldg_stream_f4(src + q);
+  }
+  uint32_t cnt = 0;
+  const bool by_depth = !ea.use_z || fs->mask_mode == 1;
+  if (by_depth) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (ok[j]) {
+        cnt += mask_keep(r[j].x, 0.0f, fs, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].y, 0.0f, fs, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].z, 0.0f, fs, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].w, 0.0f, fs, ea) ? 1u : 0u;
+      }
+  } else {
+    const NormParams np_ = fs->norm;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j)
+      if (ok[j]) {
+        const float raw[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+        for (int k = 0; k < 4; ++k) {
+          const double n = normalised_depth(raw[k], np_, ea.pc.invert);
+          cnt += mask_keep(raw[k], (float)(n * ea.pc.scale), fs, ea) ? 1u : 0u;
+        }
+      }
+  }
+  cnt = warp_sum(cnt);
+  if (lane == 0) kp.tile_state[(size_t)b * tiles_per_frame + tile] = (unsigned long long)cnt;
+}
+
+// per frame: exclusive scan of the tile counts -> high word of tile_state; total -> count[b]
+__global__ void __launch_bounds__(1024) mask_offsets_kernel(KParams kp, uint32_t *count) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (kp.state[b].status != D2PC_FRAME_READY) return;
+  unsigned long long *ts = kp.tile_state + (size_t)b * kp.emit_tiles;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < kp.emit_tiles; base += 1024u) {
+    const uint32_t i = base + (uint32_t)tid;
+    const uint32_t c = i < kp.emit_tiles ? (uint32_t)ts[i] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const uint32_t x = s_warp[w]; if (w < warp) woff += x; total += x; }
+    const uint32_t excl = s_carry + woff + incl - c;
+    if (i < kp.emit_tiles) ts[i] = ((unsigned long long)excl << 32) | (unsigned long long)c;
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) count[b] = s_carry;
+}
+
 // One tile of 1024 consecutive pixels per CTA, 4 consecutive pixels per thread (W % 4 == 0, so
 // they share a row).  NATIVE: one 16 B depth load; otherwise 4 table-driven bilinear samples of
 // the (L2-resident) low-resolution map.  MASK: depth-range / non-finite mask with ordered
@@ -118,16 +224,11 @@ template <bool NATIVE, bool MASK, bool BOUNDS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KParams kp, EmitArgs ea, FastArgs fa) {
   extern __shared__ __align__(16) float s_stage[];  // xyz [3072 + 4] | rgb [3072 + 4]
   __shared__ uint32_t s_warp[kEmitThreads / 32];
-  __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_b[6][kEmitThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
   const uint32_t t = blockIdx.x;
-  // MASK: consecutive CTAs work on different frames (tile-major order), so a frame has only
-  // in-flight/batch tiles in flight and the look-back finds an inclusive prefix within a round
-  // or two; a tile's predecessors (same frame, lower tile) still have lower CTA indices.
-  const uint32_t b = MASK ? t % fa.batch : t / fa.tiles_per_frame;
-  const uint32_t tile = MASK ? t / fa.batch : t - b * fa.tiles_per_frame;
+  const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
   FrameState *fs = kp.state + b;
   if (fs->status != D2PC_FRAME_READY) return;  // uniform per CTA (and per frame: no tile of it publishes)
   const uint32_t tile_base = tile * (uint32_t)kEmitTile;
@@ -170,11 +271,7 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       bool kk = true;
-      if (MASK) {
-        const float z = o[3 * k + 2];
-        if (ea.use_z) kk = (z >= ea.z_min) && (z <= ea.z_max);
-        if (ea.drop_nf && !is_finite_f32(raw[k])) kk = false;
-      }
+      if (MASK) kk = mask_keep(raw[k], o[3 * k + 2], fs, ea);  // same predicate as mask_count_kernel
       keep[k] = kk;
       my_cnt += kk ? 1u : 0u;
       if (BOUNDS && kk) {
@@ -227,18 +324,10 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
       total += c;
     }
     uint32_t local = warp_off + incl - my_cnt;
-    volatile unsigned long long *ts = kp.tile_state + (size_t)b * kp.emit_tiles;
-    if (warp == 0) {
-      if (lane == 0 && tile > 0) ts[tile] = (1ull << 32) | (unsigned long long)total;
-      uint32_t ex = (tile == 0) ? 0u : lookback_exclusive(ts, (int)tile);
-      if (lane == 0) {
-        ts[tile] = (2ull << 32) | (unsigned long long)(ex + total);
-        s_prefix = ex;
-        if (tile == kp.emit_tiles - 1) ea.count[b] = ex + total;
-      }
-    }
-    __syncthreads();
-    const size_t g0 = ((size_t)b * kp.g.N + s_prefix) * 3;
+    // destination row: exclusive prefix of the kept counts, computed before this launch by
+    // mask_count_kernel + mask_offsets_kernel (no inter-CTA dependency inside emit)
+    const uint32_t dest_row = (uint32_t)(kp.tile_state[(size_t)b * kp.emit_tiles + tile] >> 32);
+    const size_t g0 = ((size_t)b * kp.g.N + dest_row) * 3;
     const uint32_t s_off = (uint32_t)(g0 & 3);
     const float col[12] = {
         byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
@@ -311,11 +400,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
       col[3 * k + 0] = col[3 * k + 1] = col[3 * k + 2] = 128.0f;
     }
     bool kk = true;
-    if (MASK) {
-      const float z = o[3 * k + 2];
-      if (ea.use_z) kk = (z >= ea.z_min) && (z <= ea.z_max);
-      if (ea.drop_nf && !is_finite_f32(raw)) kk = false;
-    }
+    if (MASK) kk = mask_keep(raw, o[3 * k + 2], fs, ea);
     keep[k] = kk;
     if (kk) {
       my_cnt++;
@@ -422,7 +507,8 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
   if (workspace_bytes < make_layout(*cfg).total) return D2PC_ERR_WORKSPACE_TOO_SMALL;
   if ((((uintptr_t)d_xyz | (uintptr_t)d_rgb) & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
-  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  // emit always reads a per-pixel map: the input, or the resized map the scan materialised
+  KParams kp = per_pixel_view(make_kparams(*cfg, d_depth, d_workspace));
   EmitArgs ea;
   ea.bgr = d_bgr; ea.xyz = d_xyz; ea.rgb = d_rgb; ea.count = d_count;
   ea.pc.scale = cfg->depth_scale; ea.pc.cx = cfg->cx; ea.pc.cy = cfg->cy; ea.pc.f = cfg->f;
@@ -430,31 +516,38 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
   ea.use_z = cfg->use_z_range; ea.drop_nf = cfg->drop_nonfinite; ea.want_bounds = cfg->want_bounds;
   ea.z_min = cfg->z_min; ea.z_max = cfg->z_max;
   const bool mask = cfg->use_z_range || cfg->drop_nonfinite;
-  if (mask || cfg->want_bounds) {
-    emit_init_kernel<<<cfg->batch, 256, 0, st>>>(kp, mask ? 1 : 0);
-    D2PC_CHECK_LAUNCH();
-  }
   dim3 grid(kp.emit_tiles, cfg->batch);
   const bool fast = cfg->step == 1 && cfg->img_c == 3 && (cfg->img_w & 3) == 0 &&
-                    (((uintptr_t)d_depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) &&
+                    (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) && (kp.g.P & 3u) == 0u &&
                     ((unsigned long long)kp.g.P * (unsigned long long)cfg->img_w < (1ull << 40));
+  if (mask || cfg->want_bounds) {
+    emit_init_kernel<<<cfg->batch, 256, 0, st>>>(kp, (mask && !fast) ? 1 : 0);
+    D2PC_CHECK_LAUNCH();
+  }
+  if (mask) {
+    mask_prepare_kernel<<<cfg->batch, 32, 0, st>>>(kp, ea, consts_simple(ea.pc) ? 1 : 0);
+    D2PC_CHECK_LAUNCH();
+  }
   if (fast) {
+    if (mask) {
+      const uint32_t total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
+      mask_count_kernel<<<(total_tiles + kCountWarps - 1) / kCountWarps, kCountWarps * 32, 0, st>>>(kp, ea, kp.emit_tiles,
+                                                                                                   total_tiles);
+      D2PC_CHECK_LAUNCH();
+      mask_offsets_kernel<<<cfg->batch, 1024, 0, st>>>(kp, d_count);
+      D2PC_CHECK_LAUNCH();
+    }
     FastArgs fa;
     fa.tiles_per_frame = kp.emit_tiles;
     fa.total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
     fa.batch = (uint32_t)cfg->batch;
     fa.magic_w = ((1ull << 40) + (unsigned long long)cfg->img_w - 1ull) / (unsigned long long)cfg->img_w;
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
-    int rcl;
-    if (kp.g.native) rcl = mask ? launch_emit_fast<true, true, 5>(kp, ea, fa, st) : launch_emit_fast<true, false, 6>(kp, ea, fa, st);
-    else rcl = mask ? launch_emit_fast<false, true, 5>(kp, ea, fa, st) : launch_emit_fast<false, false, 6>(kp, ea, fa, st);
+    int rcl = mask ? launch_emit_fast<true, true, 5>(kp, ea, fa, st) : launch_emit_fast<true, false, 6>(kp, ea, fa, st);
     if (rcl) return rcl;
-  } else if (kp.g.native) {
+  } else {
     if (mask) emit_generic_kernel<true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);
     else emit_generic_kernel<true, false><<<grid, kEmitThreads, 0, st>>>(kp, ea);
-  } else {
-    if (mask) emit_generic_kernel<false, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);
-    else emit_generic_kernel<false, false><<<grid, kEmitThreads, 0, st>>>(kp, ea);
   }
   D2PC_CHECK_LAUNCH();
   if (cfg->want_bounds) {

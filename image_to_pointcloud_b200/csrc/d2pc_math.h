@@ -325,6 +325,63 @@ D2PC_HD bool consts_simple(const PixelConsts &pc) {
          fabs(pc.cy) < 1e100;
 }
 
+// float32 z the simple path emits for raw depth d (first half of simple_point)
+D2PC_HD float simple_z32(float d, const NormParams &sn, const PixelConsts &pc) {
+  double c = (double)d;
+  c = (d < sn.clip_lo_f) ? sn.p2 : c;
+  c = (d > sn.clip_hi_f) ? sn.p98 : c;
+  double a = c - sn.p2;
+  double n = patch_quotient_sign(div_by_const_fast(a, sn.den, sn.inv_den), a, sn.den);
+  if (pc.invert) n = 1.0 - n;
+  return (float)(n * pc.scale);
+}
+
+// ax-1 in depth space.  On a simple frame z32(d) is a composition of weakly monotone, correctly
+// rounded steps (clip, subtract p2, divide by den > 0, optional 1 - x, multiply by scale > 0, round
+// to float32): non-decreasing in d without invert, non-increasing with it.  Hence
+// {d : z_min <= z32(d) <= z_max} is an interval [lo, hi] of float32 values (empty if lo > hi),
+// found by bisection over the ordered float32 keys with the exact z32().  The mask then costs two
+// float compares per pixel, and a tile's kept count is known before any point is computed.
+D2PC_HD void mask_interval(const NormParams &sn, const PixelConsts &pc, float z_min, float z_max,
+                           float *lo_out, float *hi_out) {
+  const uint32_t kmin = float_to_key(-3.402823466e38f), kmax = float_to_key(3.402823466e38f);
+  const bool dec = pc.invert != 0;
+  // lower end: smallest key whose z satisfies the bound that gets TRUE as d grows
+  //   increasing z: z >= z_min ;  decreasing z: z <= z_max
+  uint32_t a = kmin, b = kmax;  // search the first key in [kmin, kmax] with pred true; kmax+1 if none
+  {
+    uint32_t lo = kmin, hi = kmax;
+    bool any = false;
+    // invariant: pred(false) for keys < lo ; if any: pred(true) for keys >= hi
+    const float zt = simple_z32(key_to_float(kmax), sn, pc);
+    any = dec ? (zt <= z_max) : (zt >= z_min);
+    if (!any) { *lo_out = 1.0f; *hi_out = 0.0f; return; }
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      const float z = simple_z32(key_to_float(mid), sn, pc);
+      const bool p = dec ? (z <= z_max) : (z >= z_min);
+      if (p) hi = mid; else lo = mid + 1u;
+    }
+    a = lo;
+  }
+  {  // upper end: largest key whose z satisfies the bound that gets FALSE as d grows
+    const float z0 = simple_z32(key_to_float(kmin), sn, pc);
+    const bool any = dec ? (z0 >= z_min) : (z0 <= z_max);
+    if (!any) { *lo_out = 1.0f; *hi_out = 0.0f; return; }
+    uint32_t lo = kmin, hi = kmax;  // find last key with pred true
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+      const float z = simple_z32(key_to_float(mid), sn, pc);
+      const bool p = dec ? (z >= z_min) : (z <= z_max);
+      if (p) lo = mid; else hi = mid - 1u;
+    }
+    b = lo;
+  }
+  if (a > b) { *lo_out = 1.0f; *hi_out = 0.0f; return; }
+  *lo_out = key_to_float(a);
+  *hi_out = key_to_float(b);
+}
+
 // ux = (double)u - cx, vy = (double)v - cy (both exact)
 D2PC_HD void simple_point(float d, double ux, double vy, const NormParams &sn, const PixelConsts &pc,
                           float *x, float *y, float *z) {

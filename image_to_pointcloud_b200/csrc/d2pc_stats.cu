@@ -243,15 +243,26 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
       uint32_t v = p / W;
       uint32_t u = p - v * W;
       TapEntry ty = kp.ytab[v];
-      for (uint32_t k = 0; k < 4u && p + k < n; ++k) {
-        if (u >= W) {
-          u -= W;
-          v += 1;
-          ty = kp.ytab[v];
+      float val[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; ++k) {
+        if (p + k < n) {
+          if (u >= W) {
+            u -= W;
+            v += 1;
+            ty = kp.ytab[v];
+          }
+          val[k] = bilinear_taps(frame, kp.g.w, kp.xtab[u], ty);
+          scan_value(val[k], Lf, Uf, b0, b1, qaddr);
+          u += 1;
         }
-        scan_value(bilinear_taps(frame, kp.g.w, kp.xtab[u], ty), Lf, Uf, b0, b1, qaddr);
-        u += 1;
       }
+      // materialise the resized map for the kernels that follow (emit, mask count, fallback)
+      float *dst = kp.resized + (size_t)b * n + p;
+      if (vec_ok && p + 3u < n) *reinterpret_cast<float4 *>(dst) = make_float4(val[0], val[1], val[2], val[3]);
+      else
+        for (uint32_t k = 0; k < 4u; ++k)
+          if (p + k < n) dst[k] = val[k];
     }
   }
 
@@ -693,7 +704,7 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   } else {
     sample_kernel<false><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
-    scan_kernel<false><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, 0);
+    scan_kernel<false><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, (kp.g.P & 3u) == 0u ? 1 : 0);
   }
   D2PC_CHECK_LAUNCH();
   select_kernel<<<dim3(2, cfg->batch), kSelThreads, select_smem, st>>>(kp);
@@ -707,19 +718,18 @@ extern "C" int d2pc_stats_fallback_enqueue(const D2pcConfig *cfg, const float *d
   if (rc) return rc;
   if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
-  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  // the scan has already materialised a resized map, so the fallback always reads a per-pixel map
+  KParams kp = per_pixel_view(make_kparams(*cfg, d_depth, d_workspace));
   dim3 grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
   fb_reset_kernel<<<cfg->batch, 32, 0, st>>>(kp);
   D2PC_CHECK_LAUNCH();
-  if (kp.g.native) fb_count_kernel<true><<<grid, kScanThreads, 0, st>>>(kp);
-  else fb_count_kernel<false><<<grid, kScanThreads, 0, st>>>(kp);
+  fb_count_kernel<true><<<grid, kScanThreads, 0, st>>>(kp);
   D2PC_CHECK_LAUNCH();
   fb_begin_kernel<<<cfg->batch, 256, 0, st>>>(kp);
   D2PC_CHECK_LAUNCH();
   for (int stage = 0; stage < 2; ++stage) {
     for (int pass = 0; pass < 4; ++pass) {
-      if (kp.g.native) fb_hist_kernel<true><<<grid, kScanThreads, 0, st>>>(kp, stage, pass);
-      else fb_hist_kernel<false><<<grid, kScanThreads, 0, st>>>(kp, stage, pass);
+      fb_hist_kernel<true><<<grid, kScanThreads, 0, st>>>(kp, stage, pass);
       D2PC_CHECK_LAUNCH();
       fb_pick_kernel<<<cfg->batch, 256, 0, st>>>(kp, pass);
       D2PC_CHECK_LAUNCH();

@@ -15,6 +15,8 @@ VARIANTS = {
     "mask4k": (2160, 3840, 2160, 3840, 8, (0.5, 9.5), "high"),
     "native4k": (2160, 3840, 2160, 3840, 8, None, "high"),
     "medium_dav2": (1080, 1920, 518, 924, 16, None, "medium"),
+    "mask4k_1": (2160, 3840, 2160, 3840, 1, (0.5, 9.5), "high"),
+    "scene4k_1": (2160, 3840, 2160, 3840, 1, (0.5, 9.5), "high"),
 }
 
 
@@ -28,6 +30,10 @@ def main():
     eng = m.FrameEngine(H, W, h, w, batch=B, device=dev)
     cfg = eng.make_config(density=dens, z_range=zr)
     depth = torch.rand((B, h, w), generator=g, device=dev) * 20
+    if name.startswith("scene"):  # smooth scene so that voxels actually merge (SURVEY 8d distribution ii)
+        vv, uu = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+        r = torch.hypot(uu - w / 2.0, vv - h / 2.0) / w
+        depth = (20.0 / (1.0 + r) + torch.randn((h, w), generator=g, device=dev) * 0.01).float().expand(B, h, w).contiguous()
     bgr = torch.randint(0, 256, (B, H, W, 3), generator=g, device=dev, dtype=torch.uint8)
     xyz, rgb = eng.alloc_outputs(cfg)
     cnt = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -41,6 +47,21 @@ def main():
     b.record()
     torch.cuda.synchronize()
     print(name, "ms/iter", a.elapsed_time(b) / iters, "kept", int(cnt.sum()), "of", B * eng.points_per_frame(cfg))
+    if len(sys.argv) > 3:  # voxel sizes: time emit(with bounds)+voxel per size
+        from image_to_pointcloud_b200.engine import EmitResult
+        cfgb = eng.make_config(density=dens, z_range=zr, want_bounds=True)
+        bounds = torch.empty((B, 6), dtype=torch.float32, device=dev)
+        for vs in [float(x) for x in sys.argv[3].split(",")]:
+            for i in range(3):
+                if i == 1:
+                    a.record()
+                eng.enqueue_stats(cfgb, depth, s)
+                eng.enqueue_emit(cfgb, depth, bgr, xyz, rgb, cnt, bounds, s)
+                res = EmitResult(xyz, rgb, cnt, bounds)
+                vx, vr, vi, vc = eng.voxel_downsample(cfgb, res, vs)
+            b.record()
+            torch.cuda.synchronize()
+            print(f"  voxel {vs}: ms/iter {a.elapsed_time(b) / 2:.3f} (stats+emit+voxel, {B} frames) voxels {int(vc.sum())} of {int(cnt.sum())} points")
 
 
 if __name__ == "__main__":

@@ -29,6 +29,9 @@ def load():
     lib.hm_depth_to_point_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hm_mask_check.restype = C.c_long
+    lib.hm_mask_check.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     return lib
 
 

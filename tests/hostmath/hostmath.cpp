@@ -104,6 +104,31 @@ long hm_depth_to_point_cloud(const uint8_t *img, int H, int W, int C, const floa
   return i;
 }
 
+// ax-1 in depth space: mask_interval() against the brute-force z-range test on the given values.
+// Returns the number of values whose interval membership differs from the z32 comparison, or -1
+// when the parameters do not describe a "simple" frame.
+long hm_mask_check(double p2, double p98, int invert, double scale, float z_min, float z_max,
+                   const float *d, long n, float *lo_out, float *hi_out) {
+  NormParams np_;
+  finalise_norm(p2, p98, 0.0f, 0.0f, false, &np_);
+  np_.median = 0.0f; np_.has_nonfinite = 0;
+  finish_norm(&np_);
+  PixelConsts pc;
+  pc.scale = scale; pc.cx = 10.0; pc.cy = 10.0; pc.f = 100.0; pc.inv_f = 1.0 / 100.0; pc.invert = invert;
+  if (!np_.simple || !consts_simple(pc)) return -1;
+  float lo, hi;
+  mask_interval(np_, pc, z_min, z_max, &lo, &hi);
+  *lo_out = lo; *hi_out = hi;
+  long bad = 0;
+  for (long i = 0; i < n; ++i) {
+    const float z = simple_z32(d[i], np_, pc);
+    const bool by_z = (z >= z_min) && (z <= z_max);
+    const bool by_d = (d[i] >= lo) && (d[i] <= hi);
+    if (by_z != by_d) bad++;
+  }
+  return bad;
+}
+
 // div_by_const(a, b, RN(1/b)) against the IEEE quotient; returns the number of mismatches
 long hm_div_check(long n, unsigned long seed, int mode) {
   std::mt19937_64 rng(seed);

@@ -99,3 +99,31 @@ def test_random_against_oracle(hm):
         p, c = harness.run_stage(hm, img, dep, **kw)
         assert_bits_equal(p, po, f"case {t} {kw}")
         assert_bits_equal(c, co, f"case {t}")
+
+
+def test_mask_interval_equals_z_range(hm):
+    """ax-1: the depth-space interval found by bisection must select exactly the values whose
+    emitted float32 z lies in [z_min, z_max] -- checked on dense value sets that include the
+    interval ends and their float32 neighbours."""
+    import ctypes as C
+    rng = np.random.default_rng(55)
+    for t in range(60):
+        p2 = float(rng.uniform(-5, 5))
+        p98 = p2 + float(np.exp(rng.uniform(-8, 4)))
+        invert = int(t % 2)
+        scale = float(rng.choice([10.0, 1.0, 37.5, 1e-3]))
+        zr = np.sort(rng.uniform(-0.1, 1.1, 2)) * scale
+        if t % 7 == 0:
+            zr = np.array([0.0, scale])       # exactly the clip ends
+        d = rng.uniform(p2 - 1.0, p98 + 1.0, 20000).astype(np.float32)
+        lo, hi = C.c_float(0), C.c_float(0)
+        bad = hm.hm_mask_check(p2, p98, invert, scale, float(np.float32(zr[0])), float(np.float32(zr[1])),
+                               d.ctypes.data, d.size, C.byref(lo), C.byref(hi))
+        assert bad == 0, (t, p2, p98, invert, scale, zr, lo.value, hi.value)
+        if lo.value <= hi.value:  # probe the ends and their neighbours
+            ends = np.array([lo.value, hi.value], np.float32)
+            probe = np.concatenate([ends, np.nextafter(ends, np.float32(-np.inf)), np.nextafter(ends, np.float32(np.inf))])
+            probe = probe[np.isfinite(probe)]
+            bad = hm.hm_mask_check(p2, p98, invert, scale, float(np.float32(zr[0])), float(np.float32(zr[1])),
+                                   probe.ctypes.data, probe.size, C.byref(lo), C.byref(hi))
+            assert bad == 0, (t, "ends")
