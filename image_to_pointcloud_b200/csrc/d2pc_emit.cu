@@ -104,10 +104,19 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 
 // ax-1 predicate.  Frames whose z is provably monotone in the raw depth (mask_mode 1) compare the
 // raw value against the frame's depth-space interval; all other frames compare the emitted z.
-__device__ __forceinline__ bool mask_keep(float raw, float z32, const FrameState *fs, const EmitArgs &ea) {
+struct MaskParams {
+  int32_t mode;
+  float lo, hi;
+};
+__device__ __forceinline__ MaskParams load_mask(const FrameState *fs) {
+  MaskParams m;
+  m.mode = fs->mask_mode; m.lo = fs->mask_lo; m.hi = fs->mask_hi;
+  return m;
+}
+__device__ __forceinline__ bool mask_keep(float raw, float z32, const MaskParams &m, const EmitArgs &ea) {
   bool kk = true;
   if (ea.use_z) {
-    if (fs->mask_mode == 1) kk = (raw >= fs->mask_lo) && (raw <= fs->mask_hi);
+    if (m.mode == 1) kk = (raw >= m.lo) && (raw <= m.hi);
     else kk = (z32 >= ea.z_min) && (z32 <= ea.z_max);
   }
   if (ea.drop_nf && !is_finite_f32(raw)) kk = false;
@@ -151,15 +160,16 @@ __global__ void __launch_bounds__(kCountWarps * 32) mask_count_kernel(KParams kp
     if (ok[j]) r[j] = ldg_stream_f4(src + q);
   }
   uint32_t cnt = 0;
-  const bool by_depth = !ea.use_z || fs->mask_mode == 1;
+  const MaskParams mp = load_mask(fs);
+  const bool by_depth = !ea.use_z || mp.mode == 1;
   if (by_depth) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (ok[j]) {
-        cnt += mask_keep(r[j].x, 0.0f, fs, ea) ? 1u : 0u;
-        cnt += mask_keep(r[j].y, 0.0f, fs, ea) ? 1u : 0u;
-        cnt += mask_keep(r[j].z, 0.0f, fs, ea) ? 1u : 0u;
-        cnt += mask_keep(r[j].w, 0.0f, fs, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].x, 0.0f, mp, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].y, 0.0f, mp, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].z, 0.0f, mp, ea) ? 1u : 0u;
+        cnt += mask_keep(r[j].w, 0.0f, mp, ea) ? 1u : 0u;
       }
   } else {
     const NormParams np_ = fs->norm;
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kCountWarps * 32) mask_count_kernel(KParams kp
         const float raw[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
         for (int k = 0; k < 4; ++k) {
           const double n = normalised_depth(raw[k], np_, ea.pc.invert);
-          cnt += mask_keep(raw[k], (float)(n * ea.pc.scale), fs, ea) ? 1u : 0u;
+          cnt += mask_keep(raw[k], (float)(n * ea.pc.scale), mp, ea) ? 1u : 0u;
         }
       }
   }
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
     const uint8_t *cp = ea.bgr + ((size_t)b * P + p0) * 3;
     c0 = ldg_stream_u32(cp); c1 = ldg_stream_u32(cp + 4); c2 = ldg_stream_u32(cp + 8);
     const NormParams np_ = fs->norm;
+    const MaskParams mp = load_mask(fs);
     if (np_.simple && fa.pc_simple) {  // uniform per frame
       const double ux0 = (double)(int32_t)u - ea.pc.cx;
       const double vy = (double)(int32_t)v - ea.pc.cy;
@@ -271,7 +282,7 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       bool kk = true;
-      if (MASK) kk = mask_keep(raw[k], o[3 * k + 2], fs, ea);  // same predicate as mask_count_kernel
+      if (MASK) kk = mask_keep(raw[k], o[3 * k + 2], mp, ea);  // same predicate as mask_count_kernel
       keep[k] = kk;
       my_cnt += kk ? 1u : 0u;
       if (BOUNDS && kk) {
@@ -372,6 +383,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
   FrameState *fs = kp.state + b;
   if (fs->status != D2PC_FRAME_READY) return;
   const NormParams np_ = fs->norm;
+  const MaskParams mp = load_mask(fs);
   const Geom &g = kp.g;
   const float *frame = kp.depth + (size_t)b * g.D;
   const uint32_t tile_base = (uint32_t)tile * (uint32_t)kEmitTile;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
       col[3 * k + 0] = col[3 * k + 1] = col[3 * k + 2] = 128.0f;
     }
     bool kk = true;
-    if (MASK) kk = mask_keep(raw, o[3 * k + 2], fs, ea);
+    if (MASK) kk = mask_keep(raw, o[3 * k + 2], mp, ea);
     keep[k] = kk;
     if (kk) {
       my_cnt++;
