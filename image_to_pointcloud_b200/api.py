@@ -79,8 +79,6 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
         img_h, img_w = image.shape[:2]
         dep_h, dep_w = depth.shape[:2]
         step = DENSITY_STEP[density]  # noqa: F841  (KeyError like the reference, before any work)
-        if smooth:
-            raise NotImplementedError("smooth=True (reference app.py:208-214) is not implemented yet")
         if image.dtype != np.uint8:
             raise TypeError("image must be uint8 (cv2.imdecode output)")
         img_c = _image_channels(image)
@@ -97,7 +95,8 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
             if img_c >= 3:
                 st["bgr_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(image)))
                 st["bgr_dev"].copy_(st["bgr_pin"], non_blocking=True)
-            res = eng.process(cfg, st["depth_dev"], st["bgr_dev"], stream=stream)
+            res = eng.process(cfg, st["depth_dev"], st["bgr_dev"], stream=stream,
+                              smooth_ksize=(smooth_ksize if smooth else None))
             if want_voxel:
                 vxyz, vrgb, vidx, vcount = eng.voxel_downsample(cfg, res, float(voxel_size),
                                                                 want_index=return_voxel_index, stream=stream)

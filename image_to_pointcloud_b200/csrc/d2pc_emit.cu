@@ -371,8 +371,67 @@ static int launch_emit_fast(const KParams &kp, const EmitArgs &ea, const FastArg
 // ------------------------------------------------------------------------------------------
 // generic path (any stride, BGRA / grey images, widths that are not a multiple of 4)
 // ------------------------------------------------------------------------------------------
-template <bool NATIVE, bool MASK>
-__global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, EmitArgs ea) {
+// a6: smoothing scratch (two float64 maps per frame) and the separable filter's column pass
+struct SmoothArgs {
+  const double *rows;  // [batch][P] row-filtered normalised map
+  int32_t ksize;
+  double k[D2PC_MAX_SMOOTH_KSIZE];
+};
+
+__device__ __forceinline__ int32_t reflect101(int32_t i, int32_t n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+// column pass of cv2's float64 separable filter: kc*x0 + sum_j k(c+j) * (x(+j) + x(-j)), no FMA
+__device__ __forceinline__ double smooth_column(const SmoothArgs &sa, const double *rows, int32_t u, int32_t v,
+                                                int32_t W, int32_t H) {
+  const int32_t r = sa.ksize >> 1;
+  double s = sa.k[r] * rows[(size_t)v * W + u];
+  for (int32_t j = 1; j <= r; ++j) {
+    const double a = rows[(size_t)reflect101(v + j, H) * W + u];
+    const double b = rows[(size_t)reflect101(v - j, H) * W + u];
+    s = s + sa.k[r + j] * (a + b);
+  }
+  return s;
+}
+
+// normalised (and inverted) map of every pixel as float64: the input of the blur (app.py:205-212)
+__global__ void __launch_bounds__(256) smooth_norm_kernel(KParams kp, int32_t invert, double *out) {
+  const int b = blockIdx.y;
+  const FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_READY) return;
+  const NormParams np_ = fs->norm;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < kp.g.P; p += gridDim.x * blockDim.x)
+    out[(size_t)b * kp.g.P + p] = normalised_depth(frame[p], np_, invert);
+}
+
+// row pass: vector body (x < W - W%4) accumulates with FMA, the scalar tail with multiply + add
+__global__ void __launch_bounds__(256) smooth_rows_kernel(KParams kp, SmoothArgs sa, const double *in, double *out) {
+  const int b = blockIdx.y;
+  if (kp.state[b].status != D2PC_FRAME_READY) return;
+  const int32_t W = kp.g.W, r = sa.ksize >> 1, wb = W - (W & 3);
+  const double *src = in + (size_t)b * kp.g.P;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < kp.g.P; p += gridDim.x * blockDim.x) {
+    const int32_t v = (int32_t)(p / (uint32_t)W), u = (int32_t)(p - (uint32_t)v * (uint32_t)W);
+    const double *row = src + (size_t)v * W;
+    double s = sa.k[0] * row[reflect101(u - r, W)];
+    if (u < wb) {
+      for (int32_t j = 1; j < sa.ksize; ++j) s = fma(sa.k[j], row[reflect101(u + j - r, W)], s);
+    } else {
+      for (int32_t j = 1; j < sa.ksize; ++j) s = s + sa.k[j] * row[reflect101(u + j - r, W)];
+    }
+    out[(size_t)b * kp.g.P + p] = s;
+  }
+}
+
+template <bool NATIVE, bool MASK, bool SMOOTH>
+__global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, EmitArgs ea, SmoothArgs sa) {
   __shared__ __align__(16) float s_xyz[kEmitTile * 3 + 4];
   __shared__ __align__(16) float s_rgb[kEmitTile * 3 + 4];
   __shared__ uint32_t s_warp[kEmitThreads / 32];
@@ -401,7 +460,8 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
     const uint32_t u = ju * (uint32_t)g.step, v = jv * (uint32_t)g.step;
     const uint32_t p = v * (uint32_t)g.W + u;
     const float raw = depth_at<NATIVE>(frame, kp, p);
-    const double n = normalised_depth(raw, np_, ea.pc.invert);
+    const double n = SMOOTH ? smooth_column(sa, sa.rows + (size_t)b * g.P, (int32_t)u, (int32_t)v, g.W, g.H)
+                            : normalised_depth(raw, np_, ea.pc.invert);
     back_project(n, (int32_t)u, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
     if (g.C >= 3) {
       const uint8_t *cp = ea.bgr + ((size_t)b * g.P + p) * (size_t)g.C;
@@ -508,11 +568,19 @@ __global__ void bounds_export_kernel(KParams kp, float *d_bounds) {
 
 using namespace d2pc;
 
-extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
-                                 void *d_workspace, size_t workspace_bytes, float *d_xyz,
-                                 float *d_rgb, uint32_t *d_count, float *d_bounds, void *stream) {
+static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr, void *d_workspace,
+                     size_t workspace_bytes, float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds,
+                     void *stream, int32_t smooth_k, const double *h_kernel, void *d_scratch, size_t scratch_bytes) {
   int rc = validate_config(cfg);
   if (rc) return rc;
+  const bool smooth = smooth_k > 0;
+  if (smooth) {
+    if ((smooth_k & 1) == 0 || smooth_k < 3 || smooth_k > D2PC_MAX_SMOOTH_KSIZE) return D2PC_ERR_UNSUPPORTED;
+    if (!h_kernel || !d_scratch) return D2PC_ERR_INVALID_ARGUMENT;
+    const size_t need = 2 * (size_t)cfg->batch * (size_t)cfg->img_h * (size_t)cfg->img_w * sizeof(double);
+    if (scratch_bytes < need) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+    if (((uintptr_t)d_scratch & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
+  }
   if (!d_workspace || !d_depth || !d_xyz || !d_rgb || !d_count) return D2PC_ERR_INVALID_ARGUMENT;
   if (cfg->img_c >= 3 && !d_bgr) return D2PC_ERR_INVALID_ARGUMENT;
   if (cfg->want_bounds && !d_bounds) return D2PC_ERR_INVALID_ARGUMENT;
@@ -529,7 +597,21 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
   ea.z_min = cfg->z_min; ea.z_max = cfg->z_max;
   const bool mask = cfg->use_z_range || cfg->drop_nonfinite;
   dim3 grid(kp.emit_tiles, cfg->batch);
-  const bool fast = cfg->step == 1 && cfg->img_c == 3 && (cfg->img_w & 3) == 0 &&
+  SmoothArgs sa;
+  sa.rows = nullptr;
+  sa.ksize = 0;
+  if (smooth) {
+    double *n64 = (double *)d_scratch, *rows = n64 + (size_t)cfg->batch * kp.g.P;
+    sa.rows = rows;
+    sa.ksize = smooth_k;
+    for (int i = 0; i < smooth_k; ++i) sa.k[i] = h_kernel[i];
+    dim3 sg(148 * 4, cfg->batch);
+    smooth_norm_kernel<<<sg, 256, 0, st>>>(kp, cfg->invert, n64);
+    D2PC_CHECK_LAUNCH();
+    smooth_rows_kernel<<<sg, 256, 0, st>>>(kp, sa, n64, rows);
+    D2PC_CHECK_LAUNCH();
+  }
+  const bool fast = !smooth && cfg->step == 1 && cfg->img_c == 3 && (cfg->img_w & 3) == 0 &&
                     (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) && (kp.g.P & 3u) == 0u &&
                     ((unsigned long long)kp.g.P * (unsigned long long)cfg->img_w < (1ull << 40));
   if (mask || cfg->want_bounds) {
@@ -537,7 +619,8 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     D2PC_CHECK_LAUNCH();
   }
   if (mask) {
-    mask_prepare_kernel<<<cfg->batch, 32, 0, st>>>(kp, ea, consts_simple(ea.pc) ? 1 : 0);
+    // a smoothed z is not a function of the pixel's own depth: exact z compare (mode 0) in that case
+    mask_prepare_kernel<<<cfg->batch, 32, 0, st>>>(kp, ea, (!smooth && consts_simple(ea.pc)) ? 1 : 0);
     D2PC_CHECK_LAUNCH();
   }
   if (fast) {
@@ -557,9 +640,12 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
     int rcl = mask ? launch_emit_fast<true, true, 5>(kp, ea, fa, st) : launch_emit_fast<true, false, 6>(kp, ea, fa, st);
     if (rcl) return rcl;
+  } else if (smooth) {
+    if (mask) emit_generic_kernel<true, true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea, sa);
+    else emit_generic_kernel<true, false, true><<<grid, kEmitThreads, 0, st>>>(kp, ea, sa);
   } else {
-    if (mask) emit_generic_kernel<true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea);
-    else emit_generic_kernel<true, false><<<grid, kEmitThreads, 0, st>>>(kp, ea);
+    if (mask) emit_generic_kernel<true, true, false><<<grid, kEmitThreads, 0, st>>>(kp, ea, sa);
+    else emit_generic_kernel<true, false, false><<<grid, kEmitThreads, 0, st>>>(kp, ea, sa);
   }
   D2PC_CHECK_LAUNCH();
   if (cfg->want_bounds) {
@@ -567,4 +653,29 @@ extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, co
     D2PC_CHECK_LAUNCH();
   }
   return D2PC_OK;
+}
+
+extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
+                                 void *d_workspace, size_t workspace_bytes, float *d_xyz,
+                                 float *d_rgb, uint32_t *d_count, float *d_bounds, void *stream) {
+  return emit_impl(cfg, d_depth, d_bgr, d_workspace, workspace_bytes, d_xyz, d_rgb, d_count, d_bounds, stream, 0,
+                   nullptr, nullptr, 0);
+}
+
+extern "C" int d2pc_smooth_scratch_bytes(const D2pcConfig *cfg, size_t *bytes) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!bytes) return D2PC_ERR_INVALID_ARGUMENT;
+  *bytes = 2 * (size_t)cfg->batch * (size_t)cfg->img_h * (size_t)cfg->img_w * sizeof(double);
+  return D2PC_OK;
+}
+
+extern "C" int d2pc_emit_smooth_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
+                                        void *d_workspace, size_t workspace_bytes, int32_t ksize,
+                                        const double *h_kernel, void *d_scratch, size_t scratch_bytes,
+                                        float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds,
+                                        void *stream) {
+  if (ksize <= 0) return D2PC_ERR_INVALID_ARGUMENT;
+  return emit_impl(cfg, d_depth, d_bgr, d_workspace, workspace_bytes, d_xyz, d_rgb, d_count, d_bounds, stream, ksize,
+                   h_kernel, d_scratch, scratch_bytes);
 }

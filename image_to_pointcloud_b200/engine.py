@@ -34,6 +34,34 @@ def reference_intrinsics(img_w: int, img_h: int, fov: Optional[float]) -> Tuple[
     return float(cx), float(cy), float(f)
 
 
+_SMALL_GAUSSIAN = {  # cv2.getGaussianKernel(k, 0, CV_64F): fixed tables for k <= 9 (sigma <= 0)
+    3: [0.25, 0.5, 0.25],
+    5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+    7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
+    9: [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256],
+}
+MAX_SMOOTH_KSIZE = 31
+
+
+def smoothing_kernel(smooth_ksize) -> list:
+    """k = max(3, int(smooth_ksize) // 2 * 2 + 1) (reference app.py:210) and the coefficients
+    cv2.GaussianBlur(d, (k, k), 0) uses: OpenCV's fixed tables up to k = 9, else
+    sigma = 0.15 k + 0.35, exp(-x^2 / (2 sigma^2)) normalised (OpenCV's getGaussianKernelBitExact)."""
+    import math
+    k = max(3, int(smooth_ksize) // 2 * 2 + 1)
+    if k in _SMALL_GAUSSIAN:
+        return list(_SMALL_GAUSSIAN[k])
+    sigma = k * 0.15 + 0.35
+    scale2x = -0.125 / (sigma * sigma)
+    vals = [math.exp(float((2 * i - (k - 1)) ** 2) * scale2x) for i in range((k - 1) // 2)]
+    total = 0.0
+    for v in vals:
+        total += v
+    mul1 = 1.0 / (total * 2.0 + 1.0)
+    half = [v * mul1 for v in vals]
+    return half + [mul1] + half[::-1]
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -71,6 +99,7 @@ class FrameEngine:
             self._any_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         assert self.workspace.data_ptr() % 256 == 0
         self._voxel_table = None
+        self._smooth_scratch = None
 
     # ---- configuration -------------------------------------------------------------------
     def make_config(self, density: str = "high", invert: bool = True, depth_scale: float = 10.0,
@@ -147,10 +176,29 @@ class FrameEngine:
                                          self.workspace_bytes, xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(),
                                          _ptr(bounds), self._stream(stream)), "d2pc_emit_enqueue")
 
+    def enqueue_emit_smooth(self, cfg: D2pcConfig, smooth_ksize, depth: torch.Tensor,
+                            bgr: Optional[torch.Tensor], xyz: torch.Tensor, rgb: torch.Tensor,
+                            count: torch.Tensor, bounds: Optional[torch.Tensor] = None, stream=None) -> None:
+        """a6: emission with cv2.GaussianBlur-compatible smoothing of the normalised map."""
+        coeffs = smoothing_kernel(smooth_ksize)
+        if len(coeffs) > MAX_SMOOTH_KSIZE:
+            raise ValueError(f"smooth_ksize too large (kernel {len(coeffs)} > {MAX_SMOOTH_KSIZE})")
+        nbytes = C.c_size_t(0)
+        check(self.lib.d2pc_smooth_scratch_bytes(C.byref(cfg), C.byref(nbytes)), "d2pc_smooth_scratch_bytes")
+        with torch.cuda.device(self.device):
+            if self._smooth_scratch is None or self._smooth_scratch.numel() < nbytes.value:
+                self._smooth_scratch = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
+        arr = (C.c_double * len(coeffs))(*coeffs)
+        check(self.lib.d2pc_emit_smooth_enqueue(C.byref(cfg), depth.data_ptr(), _ptr(bgr), self.workspace.data_ptr(),
+                                                self.workspace_bytes, len(coeffs), arr,
+                                                self._smooth_scratch.data_ptr(), self._smooth_scratch.numel(),
+                                                xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(), _ptr(bounds),
+                                                self._stream(stream)), "d2pc_emit_smooth_enqueue")
+
     # ---- whole path ----------------------------------------------------------------------
     def process(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],
                 xyz: Optional[torch.Tensor] = None, rgb: Optional[torch.Tensor] = None,
-                count: Optional[torch.Tensor] = None, stream=None) -> EmitResult:
+                count: Optional[torch.Tensor] = None, stream=None, smooth_ksize=None) -> EmitResult:
         """stats -> emit for one device-resident batch; synchronises the stream once to learn
         whether any frame needs the exact fallback, and if so runs it and re-emits those frames."""
         self._check_inputs(depth, bgr)
@@ -164,13 +212,18 @@ class FrameEngine:
                 count = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
             bounds = torch.empty((self.batch, 6), dtype=torch.float32, device=self.device) if cfg.want_bounds else None
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        def emit():
+            if smooth_ksize is None:
+                self.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, bounds, s)
+            else:
+                self.enqueue_emit_smooth(cfg, smooth_ksize, depth, bgr, xyz, rgb, count, bounds, s)
         self.enqueue_stats(cfg, depth, s)
         self.enqueue_status(cfg, s)
-        self.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, bounds, s)
+        emit()
         s.synchronize()
         if int(self._any_host[0]) != 0:
             self.enqueue_stats_fallback(cfg, depth, s)
-            self.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, bounds, s)
+            emit()
             s.synchronize()
         return EmitResult(xyz, rgb, count, bounds)
 

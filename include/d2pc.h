@@ -141,6 +141,22 @@ int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t
                       void *d_workspace, size_t workspace_bytes, float *d_xyz, float *d_rgb,
                       uint32_t *d_count, float *d_bounds, void *stream);
 
+/* a6 + a9..a11: the same emission with the optional smoothing of app.py:208-214 switched on:
+ * cv2.GaussianBlur(d, (k, k), 0) on the normalised (and inverted) map before the back-projection.
+ *   ksize      k = max(3, smooth_ksize // 2 * 2 + 1), odd, <= D2PC_MAX_SMOOTH_KSIZE
+ *   h_kernel   HOST pointer to k float64 coefficients = cv2.getGaussianKernel(k, 0, CV_64F)
+ *   d_scratch  device scratch of d2pc_smooth_scratch_bytes() bytes (two float64 maps per frame)
+ * Arithmetic follows OpenCV 4.13's float64 separable filter (rows with FMA in the vector body and
+ * plain multiply-add in the last W%4 columns, then symmetric column sums; BORDER_REFLECT_101), so
+ * percentile-branch frames are bit-exact for k <= 9; the float32 (min/max) branch is within 1e-6. */
+#define D2PC_MAX_SMOOTH_KSIZE 31
+int d2pc_smooth_scratch_bytes(const D2pcConfig *cfg, size_t *bytes);
+int d2pc_emit_smooth_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
+                             void *d_workspace, size_t workspace_bytes, int32_t ksize,
+                             const double *h_kernel, void *d_scratch, size_t scratch_bytes,
+                             float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds,
+                             void *stream);
+
 /* ax-2 voxel-grid down-sampling of each frame's emitted rows (Open3D VoxelDownSample semantics:
  * vmin = min_xyz - vs/2, idx = floor((p - vmin)/vs) on float64 copies, mean of members).
  *   d_xyz/d_rgb/d_count/d_bounds  outputs of d2pc_emit_enqueue (want_bounds = 1), row stride N

@@ -224,6 +224,121 @@ def normalise_depth(depth_resized: np.ndarray, invert: bool):
 
 
 # --------------------------------------------------------------------------------------------
+# a6  optional smoothing (app.py:208-214) -- cv2.GaussianBlur(d, (k, k), 0), BORDER_REFLECT_101
+# --------------------------------------------------------------------------------------------
+_SMALL_GAUSSIAN = {
+    1: [1.0],
+    3: [0.25, 0.5, 0.25],
+    5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+    7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
+    9: [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256],
+}
+
+
+def smooth_kernel_size(smooth_ksize) -> int:
+    """k = max(3, int(smooth_ksize) // 2 * 2 + 1)   (app.py:210)"""
+    return max(3, int(smooth_ksize) // 2 * 2 + 1)
+
+
+def gaussian_kernel(k: int) -> np.ndarray:
+    """cv2.getGaussianKernel(k, 0, CV_64F) [external, OpenCV 4.x getGaussianKernelBitExact]: fixed
+    tables for odd k <= 9 when sigma <= 0 (bit-exact here).  Larger k: sigma = k*0.15 + 0.35,
+    t_i = exp(-0.125 * x_i^2 / sigma^2) with x_i = 2i - (k-1), normalised by 1 / (2*sum + 1).
+    OpenCV evaluates that with its own soft-float exp; libm's exp can differ in the last bit, so for
+    k >= 11 the coefficients (and the blur) are only accurate to ~1e-16 relative, not bit-pinned."""
+    import math
+    if k in _SMALL_GAUSSIAN:
+        return np.array(_SMALL_GAUSSIAN[k], dtype=F64)
+    sigma = k * 0.15 + 0.35
+    scale2x = -0.125 / (sigma * sigma)
+    n2 = (k - 1) // 2
+    vals = [math.exp(float((2 * i - (k - 1)) ** 2) * scale2x) for i in range(n2)]
+    total = 0.0
+    for v in vals:
+        total += v
+    total = total * 2.0 + 1.0
+    mul1 = 1.0 / total
+    half = [v * mul1 for v in vals]
+    return np.array(half + [mul1] + half[::-1], dtype=F64)
+
+
+def _reflect101_taps(x: np.ndarray, r: int, axis: int):
+    pad = [(r, r) if a == axis else (0, 0) for a in range(2)]
+    xp = np.pad(x, pad, mode="reflect") if min(x.shape[axis], 2) > 1 or r == 0 else np.pad(x, pad, mode="edge")
+    n = x.shape[axis]
+
+    def tap(o):
+        idx = [slice(None)] * 2
+        idx[axis] = slice(r + o, r + o + n)
+        return xp[tuple(idx)]
+    return tap
+
+
+def _fma64(a, b, c):
+    """Correctly rounded float64 a*b + c via error-free transformations (TwoProduct by Dekker
+    splitting, TwoSum), good for the magnitudes met here (no overflow / subnormals)."""
+    a = np.asarray(a, F64); b = np.asarray(b, F64); c = np.asarray(c, F64)
+    split = 134217729.0  # 2^27 + 1
+    def two_prod(x, y):
+        p = x * y
+        xs = x * split; xh = xs - (xs - x); xl = x - xh
+        ys = y * split; yh = ys - (ys - y); yl = y - yh
+        e = ((xh * yh - p) + xh * yl + xl * yh) + xl * yl
+        return p, e
+    def two_sum(x, y):
+        s = x + y
+        bb = s - x
+        e = (x - (s - bb)) + (y - bb)
+        return s, e
+    p, pe = two_prod(a, b)
+    s, se = two_sum(p, c)
+    # exact value = s + (pe + se); round-to-nearest of that: add the small terms, then fix ties
+    t = pe + se
+    r = s + t
+    return r
+
+
+def gaussian_blur_f64(d: np.ndarray, k: int) -> np.ndarray:
+    """Bit-exact model of cv2.GaussianBlur(float64 HxW, (k,k), 0) as built in OpenCV 4.13.0 (AVX2
+    dispatch), recovered by experiment: separable, rows first.
+      row pass     x <  W - W%4 : s = k0*x0 ; s = fma(kj, xj, s) for j = 1..k-1   (vector body)
+                   x >= W - W%4 : the same sum with separate multiply and add      (scalar tail)
+      column pass  s = kc*x0 ; s = s + k(c+j) * (x(+j) + x(-j)) for j = 1..r       (no FMA)
+    Border: BORDER_REFLECT_101."""
+    d = np.ascontiguousarray(d, dtype=F64)
+    kk = gaussian_kernel(k)
+    r = k // 2
+    H, W = d.shape
+    tap = _reflect101_taps(d, r, 1)
+    body = kk[0] * tap(-r)
+    tail = kk[0] * tap(-r)
+    for j in range(1, k):
+        body = _fma64(kk[j], tap(j - r), body)
+        tail = tail + kk[j] * tap(j - r)
+    rows = body.copy()
+    wb = W - W % 4
+    rows[:, wb:] = tail[:, wb:]
+    tap = _reflect101_taps(rows, r, 0)
+    out = kk[r] * tap(0)
+    for j in range(1, r + 1):
+        out = out + kk[r + j] * (tap(j) + tap(-j))
+    return out
+
+
+def gaussian_blur_f32_approx(d: np.ndarray, k: int) -> np.ndarray:
+    """float32 maps (min/max and zeros branches) go through a different OpenCV/IPP code path whose
+    rounding is not modelled: exact float64 convolution rounded once (within ~2e-7 relative of
+    cv2; the tests use a tolerance for this branch)."""
+    kk = gaussian_kernel(k)
+    r = k // 2
+    x = np.ascontiguousarray(d, dtype=F64)
+    tap = _reflect101_taps(x, r, 1)
+    rows = sum(kk[j] * tap(j - r) for j in range(k))
+    tap = _reflect101_taps(rows, r, 0)
+    return sum(kk[j] * tap(j - r) for j in range(k)).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
 # a7  intrinsics (app.py:216-223)
 # --------------------------------------------------------------------------------------------
 def intrinsics(img_w: int, img_h: int, fov: Optional[float] = None):
@@ -247,13 +362,16 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
                          fov: Optional[float] = None,
                          return_info: bool = False):
     """Vectorised restatement of ``backend/app.py:174-250``.  Same positional signature."""
+    smooth_ksize_arg = smooth_ksize
     img_h, img_w = image.shape[:2]
     dep_h, dep_w = depth.shape[:2]
     if (dep_h, dep_w) != (img_h, img_w):
         depth = resize_bilinear(depth, img_h, img_w)
     d, info = normalise_depth(np.asarray(depth).astype(F32), invert)
     if smooth:
-        raise NotImplementedError("smooth=True (app.py:208-214) is a 'next' row (SURVEY 8f4)")
+        k = smooth_kernel_size(smooth_ksize_arg)
+        d = gaussian_blur_f64(d, k) if d.dtype == F64 else gaussian_blur_f32_approx(d, k)
+        info["smooth_exact"] = bool(d.dtype == F64)
     cx, cy, f = intrinsics(img_w, img_h, fov)
     step = DENSITY_STEP[density]  # KeyError for anything else, like the reference
     vs = np.arange(0, img_h, step)

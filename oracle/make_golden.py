@@ -86,6 +86,16 @@ def small_cases():
     out["neg_values"] = (img, (rng.standard_normal((24, 32)) * 100).astype(np.float32), dict(density="high"))
     out["tiny_1x1_img"] = (rng.integers(0, 256, (1, 1, 3), dtype=np.uint8),
                           np.array([[2.5]], np.float32), dict(density="high"))
+    # a6: smooth=True (cv2.GaussianBlur on the normalised map), appended last so that the random
+    # stream of the cases above is unchanged
+    out["smooth_k5_up"] = (img, dep_lo, dict(density="high", smooth=True))
+    out["smooth_k5_native_noinv"] = (img, dep_nat, dict(density="medium", smooth=True, invert=False))
+    out["smooth_k3"] = (img, dep_nat, dict(density="high", smooth=True, smooth_ksize=3))
+    out["smooth_k7_odd"] = (img_odd, dep_odd, dict(density="high", smooth=True, smooth_ksize=7))
+    out["smooth_k9_odd_low"] = (img_odd, dep_odd, dict(density="low", smooth=True, smooth_ksize=8))
+    out["smooth_zeros"] = (img, np.full((24, 32), 3.0, np.float32), dict(density="high", smooth=True))
+    d = np.full((24, 32), 3.0, np.float32); d[0, 0] = 1.0; d[5, 5] = 7.0
+    out["smooth_minmax_f32"] = (img, d, dict(density="high", smooth=True))
     return out
 
 

@@ -45,6 +45,8 @@ def test_small_goldens_bit_exact(hm, small_golden, simple):
         img, dep, kw, pts, cols = small_golden.case(name)
         if dep.shape[:2] != img.shape[:2] and min(dep.shape[:2]) < 2:
             continue
+        if kw.get("smooth"):
+            continue  # the blur runs in its own kernels (checked on the GPU and in the oracle tests)
         p, c = harness.run_stage(hm, img, dep, simple=simple, **kw)
         n_simple += hm.hm_last_simple()
         assert_bits_equal(p, pts, f"{name} points")
