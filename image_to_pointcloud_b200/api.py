@@ -39,13 +39,13 @@ def _engine_for(img_h, img_w, img_c, dep_h, dep_w, device) -> FrameEngine:
         _ENGINES[key] = eng
         with torch.cuda.device(dev):
             _STAGING[key] = dict(
-                depth_pin=torch.empty((1, dep_h, dep_w), dtype=torch.float32).pin_memory(),
+                depth_pin=torch.empty((1, dep_h, dep_w), dtype=torch.float32, pin_memory=True),
                 depth_dev=torch.empty((1, dep_h, dep_w), dtype=torch.float32, device=dev),
-                bgr_pin=(torch.empty((1, img_h, img_w, img_c), dtype=torch.uint8).pin_memory()
+                bgr_pin=(torch.empty((1, img_h, img_w, img_c), dtype=torch.uint8, pin_memory=True)
                          if img_c >= 3 else None),
                 bgr_dev=(torch.empty((1, img_h, img_w, img_c), dtype=torch.uint8, device=dev)
                          if img_c >= 3 else None),
-                count_pin=torch.zeros(1, dtype=torch.int32).pin_memory(),
+                count_pin=torch.zeros(1, dtype=torch.int32, pin_memory=True),
             )
     return eng
 
@@ -71,6 +71,7 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
                          drop_nonfinite: bool = False,
                          voxel_size: Optional[float] = None,
                          return_voxel_index: bool = False,
+                         return_bounds: bool = False,
                          device=None) -> tuple:
     """Convert a depth map to a coloured 3-D point cloud on a B200 (see module docstring)."""
     try:
@@ -86,7 +87,8 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
         st = _STAGING[(str(eng.device), int(img_h), int(img_w), img_c, int(dep_h), int(dep_w))]
         want_voxel = voxel_size is not None
         cfg = eng.make_config(density=density, invert=invert, depth_scale=float(depth_scale), fov=fov,
-                              z_range=z_range, drop_nonfinite=drop_nonfinite, want_bounds=want_voxel)
+                              z_range=z_range, drop_nonfinite=drop_nonfinite,
+                              want_bounds=(want_voxel or return_bounds))
         stream = torch.cuda.current_stream(eng.device)
         with torch.cuda.device(eng.device):
             # host -> pinned staging -> device (d = depth.astype(np.float32), app.py:191)
@@ -106,16 +108,64 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
                     out = out + (vidx[0, :n].cpu().numpy(),)
                 return out
             n = int(res.count.cpu()[0])
-            return _to_host(res.xyz[0, :n]), _to_host(res.rgb[0, :n])
+            out = (_to_host(res.xyz[0, :n]), _to_host(res.rgb[0, :n]))
+            if return_bounds:
+                out = out + (bounds_dict(res.bounds[0].cpu().numpy()),)
+            return out
     except Exception as e:  # same convention as the reference (app.py:248-250): log and re-raise
         logger.error(f"Error in point cloud generation: {str(e)}")
         raise
 
 
+DEPTH_PREVIEW_MAX = 2048  # reference backend/app.py:44
+
+
+def depth_preview_bgr(depth: np.ndarray, invert: bool = True, device=None) -> np.ndarray:
+    """Device part of the reference's create_depth_preview (app.py:127-153): robust normalisation of
+    the un-resized depth map, 8-bit quantisation and the PLASMA colour map.  uint8 [h, w, 3] BGR."""
+    d = np.ascontiguousarray(depth, dtype=np.float32)
+    h, w = d.shape[:2]
+    eng = _engine_for(int(h), int(w), 1, int(h), int(w), device)
+    with torch.cuda.device(eng.device):
+        dev = torch.from_numpy(d.reshape(1, h, w)).to(eng.device)
+        return eng.depth_preview(dev, invert=invert)[0].cpu().numpy()
+
+
+def create_depth_preview(depth: np.ndarray, invert: bool = True, device=None) -> Optional[str]:
+    """Drop-in for the reference's create_depth_preview (app.py:124-172): base64 PNG data URL of the
+    colour-mapped depth map, or None on failure (logged), like the reference.  Normalisation and
+    colour mapping run on the GPU; the optional INTER_AREA down-scale and the PNG encoder stay on the
+    host (OpenCV), as in the reference."""
+    try:
+        import base64
+
+        import cv2
+        colored = depth_preview_bgr(depth, invert=invert, device=device)
+        dh, dw = colored.shape[:2]
+        dmax = max(dh, dw)
+        if dmax > DEPTH_PREVIEW_MAX:
+            s = DEPTH_PREVIEW_MAX / float(dmax)
+            colored = cv2.resize(colored, (int(round(dw * s)), int(round(dh * s))), interpolation=cv2.INTER_AREA)
+        ok, buf = cv2.imencode('.png', colored)
+        if not ok:
+            raise ValueError("Failed to encode depth image")
+        return "data:image/png;base64," + base64.b64encode(buf.tobytes()).decode('utf-8')
+    except Exception as e:
+        logger.error(f"Failed to create depth preview: {e}")
+        return None
+
+
+def bounds_dict(b6: np.ndarray) -> dict:
+    """The "bounds" block of the reference's GIS metadata (generate_gis_metadata, app.py:393-400;
+    also the LAS offsets of save_las, app.py:352), from the min/max reduction fused into emit."""
+    return {"minX": float(b6[0]), "maxX": float(b6[3]), "minY": float(b6[1]), "maxY": float(b6[4]),
+            "minZ": float(b6[2]), "maxZ": float(b6[5])}
+
+
 def _to_host(t: torch.Tensor) -> np.ndarray:
     """Device rows -> a fresh C-contiguous float32 NumPy array (pinned host memory from torch's
     caching host allocator, so the copy runs at PCIe speed; the array owns its buffer)."""
-    host = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     host.copy_(t, non_blocking=False)
     return host.numpy()
 

@@ -655,6 +655,45 @@ static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t 
   return D2PC_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// f2 depth preview: normalise -> (d * 255).astype(uint8) -> colour map   (app.py:127-153)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preview_kernel(KParams kp, int32_t invert, const uint8_t *lut, uint8_t *out) {
+  __shared__ uint8_t s_lut[256 * 3];
+  for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const FrameState *fs = kp.state + b;
+  if (fs->status != D2PC_FRAME_READY) return;
+  const NormParams np_ = fs->norm;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  uint8_t *dst = out + (size_t)b * kp.g.P * 3;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < kp.g.P; p += gridDim.x * blockDim.x) {
+    const double n = normalised_depth(frame[p], np_, invert);
+    // float64 map in the percentile branch, float32 otherwise; astype(uint8) truncates
+    const uint32_t idx = (np_.branch == D2PC_BRANCH_PCT) ? (uint32_t)(int32_t)(n * 255.0)
+                                                        : (uint32_t)(int32_t)((float)n * 255.0f);
+    const uint32_t j = (idx & 255u) * 3u;
+    dst[3 * (size_t)p + 0] = s_lut[j];
+    dst[3 * (size_t)p + 1] = s_lut[j + 1];
+    dst[3 * (size_t)p + 2] = s_lut[j + 2];
+  }
+}
+
+extern "C" int d2pc_preview_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
+                                    size_t workspace_bytes, const uint8_t *d_lut_bgr, uint8_t *d_out_bgr,
+                                    void *stream) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!d_depth || !d_workspace || !d_lut_bgr || !d_out_bgr) return D2PC_ERR_INVALID_ARGUMENT;
+  if (cfg->dep_h != cfg->img_h || cfg->dep_w != cfg->img_w) return D2PC_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < make_layout(*cfg).total) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  preview_kernel<<<dim3(148 * 2, cfg->batch), 256, 0, (cudaStream_t)stream>>>(kp, cfg->invert, d_lut_bgr, d_out_bgr);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
 extern "C" int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
                                  void *d_workspace, size_t workspace_bytes, float *d_xyz,
                                  float *d_rgb, uint32_t *d_count, float *d_bounds, void *stream) {

@@ -96,7 +96,7 @@ class FrameEngine:
             self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
             self._status = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
             self._any = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._any_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._any_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
         assert self.workspace.data_ptr() % 256 == 0
         self._voxel_table = None
         self._smooth_scratch = None
@@ -194,6 +194,38 @@ class FrameEngine:
                                                 self._smooth_scratch.data_ptr(), self._smooth_scratch.numel(),
                                                 xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(), _ptr(bounds),
                                                 self._stream(stream)), "d2pc_emit_smooth_enqueue")
+
+    # ---- f2 depth preview ----------------------------------------------------------------
+    def depth_preview(self, depth: torch.Tensor, invert: bool = True, stream=None) -> torch.Tensor:
+        """Colour-mapped preview of every frame (reference create_depth_preview, app.py:127-153):
+        uint8 [batch, h, w, 3] BGR on the device.  The engine must have been built with the depth
+        map's own size as image size (the preview normalises the UN-resized map)."""
+        if (self.dep_h, self.dep_w) != (self.img_h, self.img_w):
+            raise ValueError("depth_preview needs an engine whose image size equals the depth size")
+        from .plasma_lut import PLASMA_BGR
+        if depth.device != self.device or depth.dtype != torch.float32 or not depth.is_contiguous() \
+                or tuple(depth.shape) != (self.batch, self.dep_h, self.dep_w):
+            raise ValueError("depth must be a contiguous float32 [batch, h, w] tensor on the engine's device")
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        cfg = self.make_config(density="high", invert=invert)
+        with torch.cuda.device(self.device):
+            if getattr(self, "_lut", None) is None:
+                self._lut = torch.tensor(PLASMA_BGR, dtype=torch.uint8, device=self.device).contiguous()
+            out = torch.empty((self.batch, self.dep_h, self.dep_w, 3), dtype=torch.uint8, device=self.device)
+
+        def run():
+            check(self.lib.d2pc_preview_enqueue(C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
+                                                self.workspace_bytes, self._lut.data_ptr(), out.data_ptr(),
+                                                s.cuda_stream), "d2pc_preview_enqueue")
+        self.enqueue_stats(cfg, depth, s)
+        self.enqueue_status(cfg, s)
+        run()
+        s.synchronize()
+        if int(self._any_host[0]) != 0:
+            self.enqueue_stats_fallback(cfg, depth, s)
+            run()
+            s.synchronize()
+        return out
 
     # ---- whole path ----------------------------------------------------------------------
     def process(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],

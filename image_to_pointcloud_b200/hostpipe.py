@@ -45,15 +45,15 @@ class HostFramePipeline:
     # -- pinned-buffer helpers ------------------------------------------------------------
     def alloc_pinned_inputs(self, n_frames: int):
         eng = self.engine
-        depths = torch.empty((n_frames, eng.dep_h, eng.dep_w), dtype=torch.float32).pin_memory()
-        images = (torch.empty((n_frames, eng.img_h, eng.img_w, eng.img_c), dtype=torch.uint8).pin_memory()
+        depths = torch.empty((n_frames, eng.dep_h, eng.dep_w), dtype=torch.float32, pin_memory=True)
+        images = (torch.empty((n_frames, eng.img_h, eng.img_w, eng.img_c), dtype=torch.uint8, pin_memory=True)
                   if eng.img_c >= 3 else None)
         return images, depths
 
     def alloc_pinned_outputs(self, n_frames: int):
-        xyz = torch.empty((n_frames, self.n_points, 3), dtype=torch.float32).pin_memory()
-        rgb = torch.empty((n_frames, self.n_points, 3), dtype=torch.float32).pin_memory()
-        counts = torch.zeros(n_frames, dtype=torch.int32).pin_memory()
+        xyz = torch.empty((n_frames, self.n_points, 3), dtype=torch.float32, pin_memory=True)
+        rgb = torch.empty((n_frames, self.n_points, 3), dtype=torch.float32, pin_memory=True)
+        counts = torch.zeros(n_frames, dtype=torch.int32, pin_memory=True)
         return xyz, rgb, counts
 
     # -- the pipeline ---------------------------------------------------------------------

@@ -157,6 +157,16 @@ int d2pc_emit_smooth_enqueue(const D2pcConfig *cfg, const float *d_depth, const 
                              float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds,
                              void *stream);
 
+/* f2 depth preview (reference create_depth_preview, app.py:124-153): the same robust normalisation
+ * on the UN-resized depth map (call d2pc_stats_enqueue first with img_h/img_w == dep_h/dep_w), then
+ * (d * 255).astype(uint8) and the colour-map lookup.
+ *   d_lut_bgr  uint8 [256, 3] colour map (COLORMAP_PLASMA, BGR)
+ *   d_out_bgr  uint8 [batch, h, w, 3]
+ * PNG encoding and the optional INTER_AREA down-scale stay on the host. */
+int d2pc_preview_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
+                         size_t workspace_bytes, const uint8_t *d_lut_bgr, uint8_t *d_out_bgr,
+                         void *stream);
+
 /* ax-2 voxel-grid down-sampling of each frame's emitted rows (Open3D VoxelDownSample semantics:
  * vmin = min_xyz - vs/2, idx = floor((p - vmin)/vs) on float64 copies, mean of members).
  *   d_xyz/d_rgb/d_count/d_bounds  outputs of d2pc_emit_enqueue (want_bounds = 1), row stride N

@@ -424,6 +424,19 @@ def depth_to_point_cloud_loop(image, depth, density="medium", invert=True, depth
 
 
 # --------------------------------------------------------------------------------------------
+# f2  depth preview (app.py:124-153), up to the colour-mapped uint8 image
+# --------------------------------------------------------------------------------------------
+def depth_preview_bgr(depth: np.ndarray, invert: bool, lut_bgr: np.ndarray) -> np.ndarray:
+    """create_depth_preview up to (and including) cv2.applyColorMap: the normalisation of
+    app.py:127-147 on the UN-resized map, ``(d * 255.0).astype(np.uint8)`` (app.py:150) and the
+    256-entry colour-map lookup (app.py:153; ``lut_bgr`` = COLORMAP_PLASMA as a [256,3] table)."""
+    d, _ = normalise_depth(np.asarray(depth).astype(F32), invert)
+    with np.errstate(invalid="ignore"):
+        img = (d * 255.0).astype(np.uint8)
+    return lut_bgr[img]
+
+
+# --------------------------------------------------------------------------------------------
 # ax-1  depth-range mask + ordered compaction  (north-star extension, parity unpinned)
 # --------------------------------------------------------------------------------------------
 def range_mask(points: np.ndarray, z_min: float, z_max: float) -> np.ndarray:

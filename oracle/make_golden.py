@@ -117,6 +117,20 @@ def main():
             store[f"{name}/colors"] = cols
             names.append(name)
             print(f"small {name:32s} N={len(pts)}")
+    # f2: depth preview data URLs of the reference's create_depth_preview (app.py:124-172)
+    from oracle.ref_loader import load_reference_module
+    refmod = load_reference_module()
+    prng = np.random.default_rng(77)
+    pnames = []
+    for pname, pd_, inv in [("preview_uniform", (prng.random((40, 56)) * 20).astype(np.float32), True),
+                            ("preview_noinv", (prng.standard_normal((33, 47)) * 3).astype(np.float32), False),
+                            ("preview_constant", np.full((16, 24), 2.0, np.float32), True)]:
+        store[f"{pname}/depth"] = pd_
+        store[f"{pname}/invert"] = np.array(inv)
+        store[f"{pname}/data_url"] = np.array(refmod.create_depth_preview(pd_, invert=inv))
+        pnames.append(pname)
+        print(f"preview {pname}")
+    store["__preview_names__"] = np.array(json.dumps(pnames))
     store["__names__"] = np.array(json.dumps(names))
     np.savez_compressed(os.path.join(GOLDEN, "small_cases.npz"), **store)
 

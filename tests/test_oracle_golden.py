@@ -139,3 +139,22 @@ def test_fmaf_exact():
         cand = [np.nextafter(lo, np.float32(-np.inf)), lo, np.nextafter(lo, np.float32(np.inf))]
         best = min(cand, key=lambda x: (abs(Fraction(float(x)) - exact), int(np.float32(x).view(np.uint32)) & 1))
         assert got[i] == best, (i, a[i], b[i], c[i], got[i], best)
+
+
+def test_depth_preview_oracle_matches_reference_data_urls(small_golden):
+    """f2: the oracle's colour-mapped preview, PNG-encoded, equals the reference's data URL."""
+    import base64
+    import json
+
+    import cv2
+    lut = np.load("tests/golden/plasma_lut_bgr.npy")
+    names = json.loads(str(small_golden.z["__preview_names__"]))
+    assert len(names) >= 3
+    for name in names:
+        dep = small_golden.z[f"{name}/depth"]
+        inv = bool(small_golden.z[f"{name}/invert"])
+        want = str(small_golden.z[f"{name}/data_url"])
+        img = O.depth_preview_bgr(dep, inv, lut)
+        ok, buf = cv2.imencode(".png", img)
+        got = "data:image/png;base64," + base64.b64encode(buf.tobytes()).decode("utf-8")
+        assert got == want, name

@@ -216,6 +216,37 @@ def test_smoothing_larger_frames(m):
         assert_bits_equal(p, po[keep], "smooth + mask")
 
 
+def test_bounds_equal_numpy_minmax(m):
+    """f4: the bounds fused into emit equal points[:, k].min()/max() (generate_gis_metadata, app.py:393-400)."""
+    rng = np.random.default_rng(39)
+    for (H, W, h, w, kw) in [(96, 160, 96, 160, dict(density="high")), (121, 161, 77, 91, dict(density="medium")),
+                             (96, 160, 96, 160, dict(density="high", z_range=(2.0, 8.0)))]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        dep = (rng.random((h, w)) * 20).astype(np.float32)
+        p, c, b = m.depth_to_point_cloud(img, dep, return_bounds=True, **kw)
+        want = {"minX": float(p[:, 0].min()), "maxX": float(p[:, 0].max()), "minY": float(p[:, 1].min()),
+                "maxY": float(p[:, 1].max()), "minZ": float(p[:, 2].min()), "maxZ": float(p[:, 2].max())}
+        assert b == want
+
+
+def test_depth_preview(m, small_golden):
+    """f2: colour-mapped preview bit-exact against the oracle; data URL equal to the reference's."""
+    import json
+    lut = np.load("tests/golden/plasma_lut_bgr.npy")
+    for name in json.loads(str(small_golden.z["__preview_names__"])):
+        dep = small_golden.z[f"{name}/depth"]
+        inv = bool(small_golden.z[f"{name}/invert"])
+        got = m.depth_preview_bgr(dep, invert=inv)
+        assert np.array_equal(got, O.depth_preview_bgr(dep, inv, lut)), name
+        assert m.create_depth_preview(dep, invert=inv) == str(small_golden.z[f"{name}/data_url"]), name
+    rng = np.random.default_rng(40)
+    for shape in [(518, 686), (200, 333)]:
+        dep = (rng.random(shape) * 20).astype(np.float32)
+        dep[3, 3] = np.nan
+        for inv in (True, False):
+            assert np.array_equal(m.depth_preview_bgr(dep, invert=inv), O.depth_preview_bgr(dep, inv, lut))
+
+
 def test_host_pipeline_matches_single_calls(m):
     rng = np.random.default_rng(37)
     H, W = 120, 200
