@@ -8,13 +8,13 @@ The package holds only what that path needs: ``csrc/`` (CUDA kernels + the C ABI
 ``include/d2pc.h``), the ctypes binding, and the host-side mirror of the reference interface.
 """
 from .api import create_depth_preview, depth_preview_bgr, depth_to_point_cloud, depth_to_point_cloud_batch
-from .engine import DENSITY_STEP, EmitResult, FrameEngine, reference_intrinsics, shard_frames
+from .engine import DENSITY_STEP, BatchStream, EmitResult, FrameEngine, reference_intrinsics, shard_frames
 from .hostpipe import HostFramePipeline
 from ._lib import D2pcConfig, D2pcError, D2pcFrameParams, load_library
 
 __all__ = [
     "depth_to_point_cloud", "depth_to_point_cloud_batch", "create_depth_preview", "depth_preview_bgr", "FrameEngine", "HostFramePipeline",
-    "EmitResult", "DENSITY_STEP", "reference_intrinsics", "shard_frames",
+    "EmitResult", "BatchStream", "DENSITY_STEP", "reference_intrinsics", "shard_frames",
     "D2pcConfig", "D2pcFrameParams", "D2pcError", "load_library",
 ]
 __version__ = "0.1.0"

@@ -302,6 +302,61 @@ class FrameEngine:
         return vxyz, vrgb, vidx, vcount
 
 
+class BatchStream:
+    """Steady-state processing of a sequence of device-resident batches on one GPU.
+
+    The statistics of batch k+1 (sample / scan / select: two of them are short single-wave kernels)
+    are enqueued on a high-priority stream while the emit of batch k (the long HBM-bound kernel)
+    runs on another, so the latency-bound launches hide behind the bandwidth-bound one.  Two
+    FrameEngines (two workspaces) alternate.  The "any frame needs the exact fallback" flags are
+    collected per batch and must be checked by the caller after ``finish()`` (``needs_fallback``);
+    flagged batches are re-run with ``FrameEngine.process``.
+    """
+
+    def __init__(self, img_h: int, img_w: int, dep_h=None, dep_w=None, *, batch: int, img_c: int = 3,
+                 device=None, **knobs):
+        self.engines = [FrameEngine(img_h, img_w, dep_h, dep_w, batch=batch, img_c=img_c, device=device)
+                        for _ in range(2)]
+        self.device = self.engines[0].device
+        self.cfg = self.engines[0].make_config(**knobs)
+        with torch.cuda.device(self.device):
+            lo, hi = torch.cuda.Stream.priority_range()
+            self.s_stats = torch.cuda.Stream(self.device, priority=hi)
+            self.s_emit = torch.cuda.Stream(self.device, priority=lo)
+            self.stats_done = [torch.cuda.Event() for _ in range(2)]
+            self.emit_done = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        self.flags = []
+
+    def submit(self, depth, bgr, xyz, rgb, count) -> None:
+        """Enqueue one batch (all arguments are device tensors of the engine's shapes)."""
+        i = self.k % 2
+        eng = self.engines[i]
+        if self.k >= 2:
+            self.s_stats.wait_event(self.emit_done[i])  # the workspace is free once emit(k-2) is done
+        eng.enqueue_stats(self.cfg, depth, self.s_stats)
+        check(eng.lib.d2pc_frame_status(C.byref(self.cfg), eng.workspace.data_ptr(), eng._status.data_ptr(),
+                                        eng._any.data_ptr(), self.s_stats.cuda_stream), "d2pc_frame_status")
+        with torch.cuda.device(self.device):
+            flag = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+            with torch.cuda.stream(self.s_stats):
+                flag.copy_(eng._any, non_blocking=True)
+        self.flags.append(flag)
+        self.stats_done[i].record(self.s_stats)
+        self.s_emit.wait_event(self.stats_done[i])
+        eng.enqueue_emit(self.cfg, depth, bgr, xyz, rgb, count, None, self.s_emit)
+        self.emit_done[i].record(self.s_emit)
+        self.k += 1
+
+    def finish(self) -> None:
+        self.s_stats.synchronize()
+        self.s_emit.synchronize()
+
+    def needs_fallback(self):
+        """Indices of submitted batches in which at least one frame was flagged (after finish())."""
+        return [j for j, f in enumerate(self.flags) if int(f[0]) != 0]
+
+
 def shard_frames(n_frames: int, world_size: int, rank: int) -> range:
     """Contiguous block partition of frame indices over ranks (one rank per GPU, no collective:
     frames are independent).  Blocks differ by at most one frame."""

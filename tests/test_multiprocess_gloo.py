@@ -1,0 +1,78 @@
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU path -- frames are sharded by
+frame with no collective on the data path; torch.distributed is only used for the barrier and the
+max-over-ranks of the timing (bench.py).  The per-frame work here is the oracle standing in for the
+device (there is no GPU in the build container)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_frames, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from image_to_pointcloud_b200.engine import shard_frames
+    from oracle import d2pc_oracle as O
+    from tests import cases
+    mine = shard_frames(n_frames, world, rank)
+    points = 0
+    sums = []
+    for i in mine:  # frame i is seeded 1000 + i on every rank
+        img = cases.make_image(12, 16, 1000 + i)
+        dep = cases.make_depth(12, 16, 1000 + i, "uniform")
+        p, c = O.depth_to_point_cloud(img, dep, density="high")
+        points += len(p)
+        sums.append(float(p[:, 2].astype(np.float64).sum()))
+    # bench.py's aggregation: barrier, max over ranks of the elapsed time, sum of the work
+    dist.barrier()
+    t = torch.tensor([1.0 + rank, float(points)], dtype=torch.float64)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (list(mine), sums))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "res.npy"), np.array([tmax[0].item(), tsum[1].item()]))
+        import json
+        json.dump(gathered, open(os.path.join(out_dir, "gathered.json"), "w"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_frame_sharding(tmp_path):
+    n_frames, world = 7, 2
+    mp.spawn(_worker, args=(world, _free_port(), n_frames, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(tmp_path / "res.npy")
+    assert res[0] == 2.0                      # max over ranks, not rank 0's own value
+    assert res[1] == n_frames * 12 * 16       # every frame processed exactly once
+    import json
+    gathered = json.load(open(tmp_path / "gathered.json"))
+    frames = [i for part, _ in gathered for i in part]
+    assert frames == list(range(n_frames))
+    # a frame's result does not depend on which rank (or how many ranks) processed it
+    sys.path.insert(0, ROOT)
+    from oracle import d2pc_oracle as O
+    from tests import cases
+    flat = [s for _, sums in gathered for s in sums]
+    for i in range(n_frames):
+        p, _ = O.depth_to_point_cloud(cases.make_image(12, 16, 1000 + i), cases.make_depth(12, 16, 1000 + i, "uniform"),
+                                      density="high")
+        assert flat[i] == float(p[:, 2].astype(np.float64).sum())
