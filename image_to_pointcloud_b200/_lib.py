@@ -16,7 +16,7 @@ EXPORTS = [
     "d2pc_abi_version", "d2pc_error_string", "d2pc_last_cuda_error", "d2pc_workspace_bytes",
     "d2pc_stats_enqueue", "d2pc_stats_fallback_enqueue", "d2pc_frame_status", "d2pc_frame_params",
     "d2pc_emit_enqueue", "d2pc_smooth_scratch_bytes", "d2pc_emit_smooth_enqueue",
-    "d2pc_preview_enqueue", "d2pc_voxel_table_bytes", "d2pc_voxel_enqueue",
+    "d2pc_preview_enqueue", "d2pc_voxel_table_bytes", "d2pc_voxel_table_init", "d2pc_voxel_enqueue",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library(path: str | None = None) -> C.CDLL:
                                              C.c_size_t, vp, vp, vp, vp, vp]
     lib.d2pc_preview_enqueue.argtypes = [cfgp, vp, vp, C.c_size_t, vp, vp, vp]
     lib.d2pc_voxel_table_bytes.argtypes = [cfgp, C.POINTER(C.c_size_t)]
+    lib.d2pc_voxel_table_init.argtypes = [cfgp, vp, C.c_size_t, vp]
     lib.d2pc_voxel_enqueue.argtypes = [cfgp, C.c_double, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -275,7 +275,7 @@ class FrameEngine:
 
     # ---- ax-2 voxel grid ------------------------------------------------------------------
     def voxel_downsample(self, cfg: D2pcConfig, res: EmitResult, voxel_size: float,
-                         want_index: bool = False, stream=None):
+                         want_index: bool = False, stream=None, check_error: bool = True):
         """Voxel-grid down-sampling of the emitted rows of every frame (needs cfg.want_bounds).
         Returns (vox_xyz [B,N,3], vox_rgb [B,N,3], vox_idx [B,N,3] or None, vox_count [B])."""
         if not cfg.want_bounds or res.bounds is None:
@@ -287,6 +287,9 @@ class FrameEngine:
         with torch.cuda.device(self.device):
             if self._voxel_table is None or self._voxel_table.numel() < nbytes.value:
                 self._voxel_table = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
+                check(self.lib.d2pc_voxel_table_init(C.byref(cfg), self._voxel_table.data_ptr(),
+                                                     self._voxel_table.numel(), self._stream(stream)),
+                      "d2pc_voxel_table_init")
             vxyz = torch.empty_like(res.xyz)
             vrgb = torch.empty_like(res.rgb)
             vidx = torch.empty(res.xyz.shape, dtype=torch.int32, device=self.device) if want_index else None
@@ -297,8 +300,12 @@ class FrameEngine:
                                           self._voxel_table.data_ptr(), self._voxel_table.numel(),
                                           vxyz.data_ptr(), vrgb.data_ptr(), _ptr(vidx), vcount.data_ptr(),
                                           verr.data_ptr(), self._stream(stream)), "d2pc_voxel_enqueue")
-        if bool((verr.cpu() != 0).any()):
-            raise ValueError("voxel_size is too small.")
+        if check_error:
+            e = verr.cpu()
+            if bool((e == 2).any()):
+                raise RuntimeError("voxel table was not initialised")
+            if bool((e != 0).any()):
+                raise ValueError("voxel_size is too small.")
         return vxyz, vrgb, vidx, vcount
 
 

@@ -169,11 +169,18 @@ int d2pc_preview_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_wo
 
 /* ax-2 voxel-grid down-sampling of each frame's emitted rows (Open3D VoxelDownSample semantics:
  * vmin = min_xyz - vs/2, idx = floor((p - vmin)/vs) on float64 copies, mean of members).
- *   d_xyz/d_rgb/d_count/d_bounds  outputs of d2pc_emit_enqueue (want_bounds = 1), row stride N
- *   d_table       scratch of d2pc_voxel_table_bytes() bytes
+ *   d_xyz/d_rgb/d_count/d_bounds  outputs of d2pc_emit_enqueue (want_bounds = 1), row stride N;
+ *                 colours must be the integral 0..255 values emit writes (their sums are kept exact)
+ *   d_table       scratch of d2pc_voxel_table_bytes() bytes, 256-byte aligned, on which
+ *                 d2pc_voxel_table_init() has run once after allocation (hash table of 64-byte
+ *                 entries + occupied-slot list).  Every d2pc_voxel_enqueue leaves it clean again.
  *   d_vox_xyz/rgb float32 [batch, N, 3]; d_vox_idx int32 [batch, N, 3] or NULL;
- *   d_vox_count   uint32 [batch]; d_vox_error int32 [batch] (1 = index overflow, >= 2^21)     */
+ *   d_vox_count   uint32 [batch]; d_vox_error int32 [batch] (1 = index overflow, >= 2^21;
+ *                 2 = table not initialised)
+ * Coordinates are summed as 64-bit fixed point of (p - vmin) (deterministic, within 2^-38 of the
+ * frame's extent of the float64 sums); frames of 2^24 rows or more return D2PC_ERR_UNSUPPORTED. */
 int d2pc_voxel_table_bytes(const D2pcConfig *cfg, size_t *bytes);
+int d2pc_voxel_table_init(const D2pcConfig *cfg, void *d_table, size_t table_bytes, void *stream);
 int d2pc_voxel_enqueue(const D2pcConfig *cfg, double voxel_size, const float *d_xyz,
                        const float *d_rgb, const uint32_t *d_count, const float *d_bounds,
                        void *d_table, size_t table_bytes, float *d_vox_xyz, float *d_vox_rgb,
