@@ -141,11 +141,13 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
 // appends the key to the CTA's staging list or bumps an equal-to-bound / non-finite counter.
 // min/max are not tracked: a frame whose percentiles collapse (p98 <= p2) goes to the exact
 // fallback, which computes them.
-struct ScanShared {
-  float pqueue[kScanPerThread][kScanThreads];  // per-thread deferred values, slot-major
+template <int QD>
+struct ScanSharedT {
+  float pqueue[QD][kScanThreads];  // per-thread deferred values, slot-major
   uint32_t qtotal[2], gbase[2];
   uint32_t red[2][kScanThreads / 32];
 };
+using ScanShared = ScanSharedT<kScanPerThread>;
 
 // Common path, 11 predicated instructions, no branch, no atomic: count "below" for both brackets
 // and, when the value is inside a bracket or non-finite (about 4% of pixels), store it in the
@@ -181,6 +183,125 @@ __device__ __forceinline__ void bracket_floats(const FrameState *fs, float Lf[2]
     Lf[br] = (L == 0u) ? -__int_as_float(0x7F800000) : key_to_float(L);           // open below
     Uf[br] = (U == 0xFFFFFFFFu) ? __int_as_float(0x7F800000) : key_to_float(U);   // open above
   }
+}
+
+// CTA totals -> 4 global atomics; deferred values -> the two brackets' raw queues
+// (queue 0: v <= U0 or non-finite; queue 1: v >= L1; a value inside both goes to both)
+template <int QD>
+__device__ __forceinline__ void scan_epilogue(ScanSharedT<QD> &sh, FrameState *fs, const KParams &kp, int b, uint32_t b0,
+                                              uint32_t b1, uint32_t qaddr, uint32_t q0, const float Lf[2],
+                                              const float Uf[2]) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t nq = (qaddr - q0) / (uint32_t)(kScanThreads * 4);
+  uint32_t n0 = 0, n1 = 0;
+  for (uint32_t j = 0; j < nq; ++j) {
+    const float v = sh.pqueue[j][tid];
+    n0 += !(v > Uf[0]) ? 1u : 0u;   // also true for NaN
+    n1 += (v >= Lf[1]) ? 1u : 0u;   // +inf lands here too; harmless (it is in queue 0 as well)
+  }
+  const uint32_t pos0 = n0 ? atomicAdd(&sh.qtotal[0], n0) : 0u;
+  const uint32_t pos1 = n1 ? atomicAdd(&sh.qtotal[1], n1) : 0u;
+  b0 = warp_sum(b0);
+  b1 = warp_sum(b1);
+  if (lane == 0) { sh.red[0][warp] = b0; sh.red[1][warp] = b1; }
+  __syncthreads();
+  if (tid < 2) {
+    uint32_t r = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) r += sh.red[tid][w];
+    if (r) atomicAdd(&fs->below[tid], r);
+  } else if (tid < 4) {
+    const uint32_t t = sh.qtotal[tid - 2];
+    sh.gbase[tid - 2] = t ? atomicAdd(&fs->nqueue[tid - 2], t) : 0u;
+  }
+  __syncthreads();
+  if (nq) {
+    float *gq0 = reinterpret_cast<float *>(kp.cand) + (size_t)b * 2 * kp.cand_cap;
+    float *gq1 = gq0 + kp.cand_cap;
+    uint32_t g0 = sh.gbase[0] + pos0, g1 = sh.gbase[1] + pos1;
+    for (uint32_t j = 0; j < nq; ++j) {
+      const float v = sh.pqueue[j][tid];
+      if (!(v > Uf[0])) { if (g0 < kp.cand_cap) gq0[g0] = v; ++g0; }
+      if (v >= Lf[1]) { if (g1 < kp.cand_cap) gq1[g1] = v; ++g1; }
+    }
+  }
+}
+
+// Resized depth, up-scaling geometry: one CTA owns a kRzRows x kRzCols tile of the (H x W) map.
+// The horizontal lerp of every source row the tile needs is computed once into shared memory
+// (a source row feeds ~1/scale_y destination rows), then each thread finishes 4 consecutive
+// columns of a row with one vertical lerp from two LDS.128, scans them and writes the resized map
+// with one 16 B store.  Same arithmetic as bilinear_taps (horizontal fmaf, then vertical fmaf;
+// clamped taps copy; corner blocks turn +-inf into NaN).
+constexpr int kRzCols = 128, kRzRows = 32, kRzSrcRows = 40;
+constexpr int kRzPerThread = kRzCols * kRzRows / kScanThreads;  // 16
+
+__global__ void __launch_bounds__(kScanThreads) scan_resized_tiled_kernel(KParams kp) {
+  __shared__ ScanSharedT<kRzPerThread> sh;
+  __shared__ __align__(16) float s_h[kRzSrcRows][kRzCols];
+  const int b = blockIdx.z, tid = threadIdx.x;
+  FrameState *fs = kp.state + b;
+  const float *frame = kp.depth + (size_t)b * kp.g.D;
+  const int32_t W = kp.g.W, H = kp.g.H, sw = kp.g.w;
+  float Lf[2], Uf[2];
+  bracket_floats(fs, Lf, Uf);
+  if (tid < 2) sh.qtotal[tid] = 0;
+  uint32_t b0 = 0, b1 = 0;
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sh.pqueue[0][tid]);
+  uint32_t qaddr = q0;
+  const int32_t u0 = blockIdx.x * kRzCols, v0 = blockIdx.y * kRzRows;
+  const int32_t rows = min(kRzRows, H - v0);
+  const int32_t ys = kp.ytab[v0].i0c & 0x7FFFFFFF;
+  const TapEntry tl = kp.ytab[v0 + rows - 1];
+  const int32_t nsr = (tl.i0c & 0x7FFFFFFF) + (tl.i0c < 0 ? 0 : 1) - ys + 1;  // <= kRzSrcRows (host checked)
+  {  // phase 1: horizontally resized source rows of this tile
+    const int32_t col = tid & (kRzCols - 1), u = u0 + col;
+    if (u < W) {
+      const TapEntry tx = kp.xtab[u];
+      const int32_t x0 = tx.i0c & 0x7FFFFFFF;
+      const bool cx = tx.i0c < 0;
+      for (int32_t r = tid / kRzCols; r < nsr; r += kScanThreads / kRzCols) {
+        const float *row = frame + (size_t)(ys + r) * sw;
+        const float a = __ldg(row + x0);
+        float h = a;
+        if (!cx) h = fmaf(__ldg(row + x0 + 1) - a, tx.t, a);
+        s_h[r][col] = h;
+      }
+    }
+  }
+  __syncthreads();
+  {  // phase 2: vertical lerp, scan, materialise
+    const int32_t c4 = (tid & 31) * 4, uu = u0 + c4, warp = tid >> 5;
+    if (uu < W) {  // W % 4 == 0: the four columns are inside together
+      bool cxk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cxk[k] = kp.xtab[uu + k].i0c < 0;
+#pragma unroll 1
+      for (int32_t rr = warp; rr < rows; rr += kScanThreads / 32) {
+        const int32_t v = v0 + rr;
+        const TapEntry ty = kp.ytab[v];
+        const int32_t y0 = (ty.i0c & 0x7FFFFFFF) - ys;
+        const float4 r0 = *reinterpret_cast<const float4 *>(&s_h[y0][c4]);
+        float o[4] = {r0.x, r0.y, r0.z, r0.w};
+        if (ty.i0c < 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (cxk[k] && is_inf_f32(o[k])) o[k] = nan_f32();
+        } else {
+          const float4 r1 = *reinterpret_cast<const float4 *>(&s_h[y0 + 1][c4]);
+          o[0] = fmaf(r1.x - r0.x, ty.t, r0.x);
+          o[1] = fmaf(r1.y - r0.y, ty.t, r0.y);
+          o[2] = fmaf(r1.z - r0.z, ty.t, r0.z);
+          o[3] = fmaf(r1.w - r0.w, ty.t, r0.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scan_value(o[k], Lf, Uf, b0, b1, qaddr);
+        float *dst = kp.resized + (size_t)b * kp.g.P + (size_t)v * W + uu;
+        *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  scan_epilogue(sh, fs, kp, b, b0, b1, qaddr, q0, Lf, Uf);
 }
 
 template <bool NATIVE>
@@ -266,41 +387,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
     }
   }
 
-  // epilogue: CTA totals -> 4 global atomics; deferred values -> the two brackets' raw queues
-  // (queue 0: v <= U0 or non-finite; queue 1: v >= L1; a value inside both goes to both)
-  const int lane = tid & 31, warp = tid >> 5;
-  const uint32_t nq = (qaddr - q0) / (uint32_t)(kScanThreads * 4);
-  uint32_t n0 = 0, n1 = 0;
-  for (uint32_t j = 0; j < nq; ++j) {
-    const float v = sh.pqueue[j][tid];
-    n0 += !(v > Uf[0]) ? 1u : 0u;   // also true for NaN
-    n1 += (v >= Lf[1]) ? 1u : 0u;   // +inf lands here too; harmless (it is in queue 0 as well)
-  }
-  const uint32_t pos0 = n0 ? atomicAdd(&sh.qtotal[0], n0) : 0u;
-  const uint32_t pos1 = n1 ? atomicAdd(&sh.qtotal[1], n1) : 0u;
-  b0 = warp_sum(b0);
-  b1 = warp_sum(b1);
-  if (lane == 0) { sh.red[0][warp] = b0; sh.red[1][warp] = b1; }
-  __syncthreads();
-  if (tid < 2) {
-    uint32_t r = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) r += sh.red[tid][w];
-    if (r) atomicAdd(&fs->below[tid], r);
-  } else if (tid < 4) {
-    const uint32_t t = sh.qtotal[tid - 2];
-    sh.gbase[tid - 2] = t ? atomicAdd(&fs->nqueue[tid - 2], t) : 0u;
-  }
-  __syncthreads();
-  if (nq) {
-    float *gq0 = reinterpret_cast<float *>(kp.cand) + (size_t)b * 2 * kp.cand_cap;
-    float *gq1 = gq0 + kp.cand_cap;
-    uint32_t g0 = sh.gbase[0] + pos0, g1 = sh.gbase[1] + pos1;
-    for (uint32_t j = 0; j < nq; ++j) {
-      const float v = sh.pqueue[j][tid];
-      if (!(v > Uf[0])) { if (g0 < kp.cand_cap) gq0[g0] = v; ++g0; }
-      if (v >= Lf[1]) { if (g1 < kp.cand_cap) gq1[g1] = v; ++g1; }
-    }
-  }
+  scan_epilogue(sh, fs, kp, b, b0, b1, qaddr, q0, Lf, Uf);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -704,7 +791,19 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   } else {
     sample_kernel<false><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
-    scan_kernel<false><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, (kp.g.P & 3u) == 0u ? 1 : 0);
+    // tiled kernel: needs 16 B-aligned rows of the resized map and every tile's source rows in shared memory
+    bool tiled = (kp.g.W & 3) == 0;
+    for (int32_t v0 = 0; tiled && v0 < kp.g.H; v0 += kRzRows) {
+      const int32_t v1 = (v0 + kRzRows < kp.g.H ? v0 + kRzRows : kp.g.H) - 1;
+      const AxisTap t0 = axis_tap(v0, kp.g.scale_y, kp.g.h), t1 = axis_tap(v1, kp.g.scale_y, kp.g.h);
+      if (t1.i1 - t0.i0 + 1 > kRzSrcRows) tiled = false;
+    }
+    if (tiled) {
+      dim3 tg((kp.g.W + kRzCols - 1) / kRzCols, (kp.g.H + kRzRows - 1) / kRzRows, cfg->batch);
+      scan_resized_tiled_kernel<<<tg, kScanThreads, 0, st>>>(kp);
+    } else {
+      scan_kernel<false><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, (kp.g.P & 3u) == 0u ? 1 : 0);
+    }
   }
   D2PC_CHECK_LAUNCH();
   select_kernel<<<dim3(2, cfg->batch), kSelThreads, select_smem, st>>>(kp);

@@ -130,6 +130,28 @@ def test_resized_batch_all_strides(m):
             assert_bits_equal(res.rgb[b].cpu().numpy(), co, f"{dens} frame {b}")
 
 
+def test_resized_tiled_scan_geometries(m):
+    """Widths that are a multiple of 4 take the shared-memory tiled resize (up- and mild down-scaling);
+    strong down-scaling falls back to the direct kernel.  Non-finite values sit on corners and edges."""
+    rng = np.random.default_rng(41)
+    for (H, W, h, w) in [(200, 320, 77, 91), (96, 160, 100, 170), (130, 256, 37, 300), (64, 132, 200, 260),
+                         (33, 4, 10, 3), (480, 640, 518, 686)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        deps = [(rng.random((h, w)) * 20).astype(np.float32) for _ in range(2)]
+        deps[1][0, 0] = np.inf
+        deps[1][h - 1, w - 1] = -np.inf
+        deps[1][0, w // 2] = np.nan
+        deps[1][h // 2, 0] = np.inf
+        eng, cfg, res = _engine_run(m, [img, img], deps, density="high")
+        for b in range(2):
+            po, co = _oracle(img, deps[b], density="high")
+            assert_bits_equal(res.xyz[b].cpu().numpy(), po, f"{(H, W, h, w)} frame {b}")
+        po, co = _oracle(img, deps[0], density="medium", invert=False)
+        p, c = m.depth_to_point_cloud(img, deps[0], density="medium", invert=False, z_range=(1.0, 9.0))
+        keep = O.range_mask(po, 1.0, 9.0)
+        assert_bits_equal(p, po[keep], f"{(H, W, h, w)} masked medium")
+
+
 def test_percentile_selection_on_hard_distributions(m):
     """Exact order statistics for sizes above the sampling threshold, incl. ReLU-style zeros."""
     rng = np.random.default_rng(34)
