@@ -218,9 +218,10 @@ __global__ void __launch_bounds__(1024) mask_offsets_kernel(KParams kp, uint32_t
   if (tid == 0) count[b] = s_carry;
 }
 
-// One tile of 1024 consecutive pixels per CTA, 4 consecutive pixels per thread (W % 4 == 0, so
-// they share a row).  NATIVE: one 16 B depth load; otherwise 4 table-driven bilinear samples of
-// the (L2-resident) low-resolution map.  MASK: depth-range / non-finite mask with ordered
+// One tile of 1024 consecutive output rows per CTA, 4 consecutive rows per thread (they share an
+// image row).  STEP 1: one 16 B depth load + 12 colour bytes; STEP 2 / 4 (density medium / low):
+// the same tiling over the strided output grid, loading only the sectors that hold sampled
+// pixels.  The depth map is always per-pixel here (the scan materialises a resized map).  MASK: depth-range / non-finite mask with ordered
 // compaction (CTA scan + decoupled look-back over the frame's tiles, tiles dispatched in order).
 // High occupancy matters more than per-thread ILP here (measured: 6 CTAs/SM beat 3-5 and beat a
 // persistent register-prefetching variant), hence MIN_BLOCKS.
@@ -230,19 +231,21 @@ struct FastArgs {
   int32_t pc_simple;
 };
 
-template <bool NATIVE, bool MASK, bool BOUNDS, int MIN_BLOCKS>
+template <int STEP, bool MASK, bool BOUNDS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KParams kp, EmitArgs ea, FastArgs fa) {
+  static_assert(STEP == 1 || !MASK, "the masked fast path is stride 1 only");
   extern __shared__ __align__(16) float s_stage[];  // xyz [3072 + 4] | rgb [3072 + 4]
   __shared__ uint32_t s_warp[kEmitThreads / 32];
   __shared__ uint32_t s_b[6][kEmitThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t P = kp.g.P, W = (uint32_t)kp.g.W;
+  // P = rows of the output grid (nu x nv); for STEP 1 the grid is the image itself
+  const uint32_t P = kp.g.N, W = (uint32_t)kp.g.W, NU = (uint32_t)kp.g.nu;
   const uint32_t t = blockIdx.x;
   const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
   FrameState *fs = kp.state + b;
   if (fs->status != D2PC_FRAME_READY) return;  // uniform per CTA (and per frame: no tile of it publishes)
   const uint32_t tile_base = tile * (uint32_t)kEmitTile;
-  const uint32_t p0 = tile_base + 4u * (uint32_t)tid;
+  const uint32_t p0 = tile_base + 4u * (uint32_t)tid;   // first of this thread's 4 output rows
   float *s_xyz = s_stage;
   float *s_rgb = s_stage + (kEmitTile * 3 + 4);
   float o[12];
@@ -251,19 +254,38 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
   uint32_t my_cnt = 0;
   uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
   if (p0 < P) {
-    const uint32_t v = (uint32_t)(((unsigned long long)p0 * fa.magic_w) >> 40), u = p0 - v * W;
+    // (jv, ju) in the output grid; magic_w divides by nu (== W for STEP 1)
+    const uint32_t jv = (uint32_t)(((unsigned long long)p0 * fa.magic_w) >> 40), ju = p0 - jv * NU;
+    const uint32_t v = jv * (uint32_t)STEP, u = ju * (uint32_t)STEP;
+    const size_t pix = (size_t)b * kp.g.P + (size_t)v * W + u;  // first source pixel (same row for all 4)
     float raw[4];
-    if (NATIVE) {
-      const float4 d4 = ldg_stream_f4(kp.depth + (size_t)b * P + p0);
+    const uint8_t *cp = ea.bgr + pix * 3;
+    if (STEP == 1) {
+      const float4 d4 = ldg_stream_f4(kp.depth + pix);
       raw[0] = d4.x; raw[1] = d4.y; raw[2] = d4.z; raw[3] = d4.w;
+      c0 = ldg_stream_u32(cp); c1 = ldg_stream_u32(cp + 4); c2 = ldg_stream_u32(cp + 8);
+    } else if (STEP == 2) {
+      // pixels u, u+2, u+4, u+6: two 16 B depth loads, the 24 colour bytes of 8 pixels
+      const float4 da = ldg_stream_f4(kp.depth + pix), db = ldg_stream_f4(kp.depth + pix + 4);
+      raw[0] = da.x; raw[1] = da.z; raw[2] = db.x; raw[3] = db.z;
+      const uint32_t w0 = ldg_stream_u32(cp), w1 = ldg_stream_u32(cp + 4), w2 = ldg_stream_u32(cp + 8);
+      const uint32_t w3 = ldg_stream_u32(cp + 12), w4 = ldg_stream_u32(cp + 16), w5 = ldg_stream_u32(cp + 20);
+      // repack as the STEP 1 layout: c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
+      const uint32_t px1 = __byte_perm(w1, w2, 0x0432);  // bytes 6,7,8   -> B1 G1 R1 .
+      const uint32_t px3 = __byte_perm(w4, w5, 0x0432);  // bytes 18,19,20 -> B3 G3 R3 .
+      c0 = __byte_perm(w0, px1, 0x4210);                 // B0 G0 R0 B1
+      c1 = __byte_perm(px1, w3, 0x5421);                 // G1 R1 B2 G2
+      c2 = __byte_perm(w3, px3, 0x6542);                 // R2 B3 G3 R3
     } else {
-      const float *frame = kp.depth + (size_t)b * kp.g.D;
-      const TapEntry ty = kp.ytab[v];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) raw[k] = bilinear_taps(frame, kp.g.w, kp.xtab[u + k], ty);
+      // pixels u, u+4, u+8, u+12: one 4 B load each (12-byte colour pitch keeps u32 loads aligned)
+      raw[0] = __ldg(kp.depth + pix); raw[1] = __ldg(kp.depth + pix + 4);
+      raw[2] = __ldg(kp.depth + pix + 8); raw[3] = __ldg(kp.depth + pix + 12);
+      const uint32_t q0 = ldg_stream_u32(cp), q1 = ldg_stream_u32(cp + 12), q2 = ldg_stream_u32(cp + 24),
+                     q3 = ldg_stream_u32(cp + 36);
+      c0 = __byte_perm(q0, q1, 0x4210);   // B0 G0 R0 B1
+      c1 = __byte_perm(q1, q2, 0x5421);   // G1 R1 B2 G2
+      c2 = __byte_perm(q2, q3, 0x6542);   // R2 B3 G3 R3
     }
-    const uint8_t *cp = ea.bgr + ((size_t)b * P + p0) * 3;
-    c0 = ldg_stream_u32(cp); c1 = ldg_stream_u32(cp + 4); c2 = ldg_stream_u32(cp + 8);
     const NormParams np_ = fs->norm;
     const MaskParams mp = load_mask(fs);
     if (np_.simple && fa.pc_simple) {  // uniform per frame
@@ -271,12 +293,12 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
       const double vy = (double)(int32_t)v - ea.pc.cy;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        simple_point(raw[k], ux0 + (double)k, vy, np_, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+        simple_point(raw[k], ux0 + (double)(k * STEP), vy, np_, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const double n = normalised_depth(raw[k], np_, ea.pc.invert);
-        back_project(n, (int32_t)u + k, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
+        back_project(n, (int32_t)u + k * STEP, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
       }
     }
 #pragma unroll
@@ -360,11 +382,11 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
   if (BOUNDS) reduce_bounds(fs, mn, mx, s_b);
 }
 
-template <bool NATIVE, bool MASK, int MIN_BLOCKS>
+template <int STEP, bool MASK, int MIN_BLOCKS>
 static int launch_emit_fast(const KParams &kp, const EmitArgs &ea, const FastArgs &fa, cudaStream_t st) {
   const size_t smem = 2 * ((size_t)kEmitTile * 3 + 4) * sizeof(float);
-  if (ea.want_bounds) emit_fast_kernel<NATIVE, MASK, true, 5><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
-  else emit_fast_kernel<NATIVE, MASK, false, MIN_BLOCKS><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
+  if (ea.want_bounds) emit_fast_kernel<STEP, MASK, true, 5><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
+  else emit_fast_kernel<STEP, MASK, false, MIN_BLOCKS><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
   return D2PC_OK;
 }
 
@@ -611,9 +633,11 @@ static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t 
     smooth_rows_kernel<<<sg, 256, 0, st>>>(kp, sa, n64, rows);
     D2PC_CHECK_LAUNCH();
   }
-  const bool fast = !smooth && cfg->step == 1 && cfg->img_c == 3 && (cfg->img_w & 3) == 0 &&
-                    (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) && (kp.g.P & 3u) == 0u &&
-                    ((unsigned long long)kp.g.P * (unsigned long long)cfg->img_w < (1ull << 40));
+  // fast path: 3-channel image, 4 consecutive output rows per thread in one image row, vector loads.
+  // stride 1: W % 4 == 0; stride 2: W % 8 == 0; stride 4: W % 16 == 0 (unmasked only for strides > 1)
+  const bool fast = !smooth && cfg->img_c == 3 && (cfg->img_w % (4 * cfg->step)) == 0 && (cfg->step == 1 || !mask) &&
+                    (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) && (kp.g.N & 3u) == 0u &&
+                    ((unsigned long long)kp.g.N * (unsigned long long)kp.g.nu < (1ull << 40));
   if (mask || cfg->want_bounds) {
     emit_init_kernel<<<cfg->batch, 256, 0, st>>>(kp, (mask && !fast) ? 1 : 0);
     D2PC_CHECK_LAUNCH();
@@ -636,9 +660,13 @@ static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t 
     fa.tiles_per_frame = kp.emit_tiles;
     fa.total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
     fa.batch = (uint32_t)cfg->batch;
-    fa.magic_w = ((1ull << 40) + (unsigned long long)cfg->img_w - 1ull) / (unsigned long long)cfg->img_w;
+    fa.magic_w = ((1ull << 40) + (unsigned long long)kp.g.nu - 1ull) / (unsigned long long)kp.g.nu;
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
-    int rcl = mask ? launch_emit_fast<true, true, 5>(kp, ea, fa, st) : launch_emit_fast<true, false, 6>(kp, ea, fa, st);
+    int rcl;
+    if (mask) rcl = launch_emit_fast<1, true, 5>(kp, ea, fa, st);
+    else if (cfg->step == 1) rcl = launch_emit_fast<1, false, 6>(kp, ea, fa, st);
+    else if (cfg->step == 2) rcl = launch_emit_fast<2, false, 6>(kp, ea, fa, st);
+    else rcl = launch_emit_fast<4, false, 6>(kp, ea, fa, st);
     if (rcl) return rcl;
   } else if (smooth) {
     if (mask) emit_generic_kernel<true, true, true><<<grid, kEmitThreads, 0, st>>>(kp, ea, sa);

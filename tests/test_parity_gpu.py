@@ -152,6 +152,26 @@ def test_resized_tiled_scan_geometries(m):
         assert_bits_equal(p, po[keep], f"{(H, W, h, w)} masked medium")
 
 
+def test_strided_fast_emit(m):
+    """density medium / low on widths that are multiples of 8 / 16 take the vectorised strided path;
+    other widths the generic one.  Both must match the oracle bit for bit (incl. the fused bounds)."""
+    rng = np.random.default_rng(42)
+    for (H, W, h, w) in [(120, 320, 120, 320), (121, 336, 60, 100), (64, 1040, 64, 1040), (50, 24, 50, 24),
+                         (37, 48, 37, 48)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        dep = (rng.random((h, w)) * 20).astype(np.float32)
+        for dens in ("medium", "low"):
+            for inv in (True, False):
+                po, co = _oracle(img, dep, density=dens, invert=inv)
+                p, c, bd = m.depth_to_point_cloud(img, dep, density=dens, invert=inv, return_bounds=True)
+                assert_bits_equal(p, po, f"{(H, W)} {dens} invert={inv}")
+                assert_bits_equal(c, co, f"{(H, W)} {dens} colours")
+                assert bd["minX"] == float(po[:, 0].min()) and bd["maxZ"] == float(po[:, 2].max())
+                p, c = m.depth_to_point_cloud(img, dep, density=dens, invert=inv)
+                assert_bits_equal(p, po, f"{(H, W)} {dens} invert={inv} (no bounds)")
+                assert_bits_equal(c, co, f"{(H, W)} {dens} colours (no bounds)")
+
+
 def test_percentile_selection_on_hard_distributions(m):
     """Exact order statistics for sizes above the sampling threshold, incl. ReLU-style zeros."""
     rng = np.random.default_rng(34)
