@@ -403,14 +403,15 @@ def run_extras(m, device):
 
     g = torch.Generator(device=device)
     g.manual_seed(5)
-    for name, (H, W, h, w, B, zr) in {
-        "1080p_dav2_depth_518x924": (1080, 1920, 518, 924, 16, None),
-        "1080p_native_zrange_0.5_9.5": (1080, 1920, 1080, 1920, 16, (0.5, 9.5)),
-        "4k_native": (2160, 3840, 2160, 3840, 8, None),
-        "4k_native_zrange_0.5_9.5": (2160, 3840, 2160, 3840, 8, (0.5, 9.5)),
+    for name, (H, W, h, w, B, zr, dens) in {
+        "1080p_dav2_depth_518x924": (1080, 1920, 518, 924, 64, None, "high"),
+        "1080p_dav2_depth_density_medium (what the reference UI runs)": (1080, 1920, 518, 924, 64, None, "medium"),
+        "1080p_native_zrange_0.5_9.5": (1080, 1920, 1080, 1920, 64, (0.5, 9.5), "high"),
+        "4k_native": (2160, 3840, 2160, 3840, 16, None, "high"),
+        "4k_native_zrange_0.5_9.5": (2160, 3840, 2160, 3840, 16, (0.5, 9.5), "high"),
     }.items():
         eng = m.FrameEngine(H, W, h, w, batch=B, device=device)
-        cfg = eng.make_config(density="high", z_range=zr)
+        cfg = eng.make_config(density=dens, z_range=zr)
         depth = torch.rand((B, h, w), generator=g, device=device) * 20
         bgr = torch.randint(0, 256, (B, H, W, 3), generator=g, device=device, dtype=torch.uint8)
         xyz, rgb = eng.alloc_outputs(cfg)
@@ -422,11 +423,16 @@ def run_extras(m, device):
             eng.enqueue_emit(cfg, depth, bgr, xyz, rgb, cnt, None, s)
         ms = timeit(step)
         kept = int(cnt.sum())
-        alg = B * (4 * h * w + 3 * H * W) + 24 * kept
-        out[name] = {"ms_per_step": round(ms, 4), "frames": B, "mpoints_in_per_s": round(B * H * W / ms / 1e3, 1),
-                     "kept_fraction": round(kept / (B * H * W), 4), "alg_gbs": round(alg / ms / 1e6, 1)}
+        n_frame = eng.points_per_frame(cfg)
+        alg = B * (4 * h * w + 3 * n_frame) + 24 * kept   # 4 D + 3 N + 24 N_out per frame
+        out[name] = {"ms_per_step": round(ms, 4), "frames": B, "mpoints_out_per_s": round(kept / ms / 1e3, 1),
+                     "images_per_s": round(B / ms * 1e3, 1), "kept_fraction": round(kept / (B * n_frame), 4),
+                     "alg_gbs": round(alg / ms / 1e6, 1)}
         del eng, depth, bgr, xyz, rgb
         torch.cuda.empty_cache()
+    # BASELINE configs[2] / [4]: 4K frame, depth-range mask, voxel-size sweep (voxel stage alone)
+    from profiles.voxel_sweep import sweep
+    out["4k_zrange_voxel_sweep"] = sweep(iters=5, peak=measured_peak()[0])
     return out
 
 

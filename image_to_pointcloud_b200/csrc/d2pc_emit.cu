@@ -123,16 +123,59 @@ __device__ __forceinline__ bool mask_keep(float raw, float z32, const MaskParams
   return kk;
 }
 
-__global__ void mask_prepare_kernel(KParams kp, EmitArgs ea, int pc_simple) {
+// mask_interval (d2pc_math.h) by one warp: 32 probes of the ordered key space per round instead of
+// one, so the two searches take ~7 rounds each.  The predicate is monotone (false -> true).
+template <typename Pred>
+__device__ __forceinline__ uint32_t warp_first_true(uint32_t lo, uint32_t hi, Pred pred) {
+  // invariant: pred is false for keys < lo and true for hi
+  const int lane = threadIdx.x & 31;
+  while (lo < hi) {
+    const unsigned long long span = (unsigned long long)(hi - lo);
+    const uint32_t k = lo + (uint32_t)((span * (unsigned long long)(lane + 1)) / 33ull);  // < hi
+    const bool p = pred(k);
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (m == 0u) {
+      lo = __shfl_sync(0xffffffffu, k, 31) + 1u;
+    } else {
+      const int j = __ffs(m) - 1;
+      hi = __shfl_sync(0xffffffffu, k, j);
+      if (j > 0) lo = __shfl_sync(0xffffffffu, k, j - 1) + 1u;
+    }
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(32) mask_prepare_kernel(KParams kp, EmitArgs ea, int pc_simple) {
   FrameState *fs = kp.state + blockIdx.x;
-  if (threadIdx.x != 0 || fs->status != D2PC_FRAME_READY) return;
-  fs->mask_mode = 0;
-  if (ea.use_z && fs->norm.simple && pc_simple) {
-    float lo, hi;
-    mask_interval(fs->norm, ea.pc, ea.z_min, ea.z_max, &lo, &hi);
-    fs->mask_lo = lo;
-    fs->mask_hi = hi;
-    fs->mask_mode = 1;
+  if (fs->status != D2PC_FRAME_READY) return;
+  const bool by_depth = ea.use_z && fs->norm.simple && pc_simple;  // uniform over the warp
+  float lo_f = 1.0f, hi_f = 0.0f;  // empty interval
+  if (by_depth) {
+    const NormParams sn = fs->norm;
+    const uint32_t kmin = float_to_key(-3.402823466e38f), kmax = float_to_key(3.402823466e38f);
+    const bool dec = ea.pc.invert != 0;
+    // z32(d) is monotone in d (see mask_interval): the kept set is the key interval [a, b]
+    //   a = first key whose z passes the bound that turns TRUE as d grows
+    //   b = last key whose z passes the bound that turns FALSE as d grows = first failing key - 1
+    auto rising = [&](uint32_t k) {
+      const float z = simple_z32(key_to_float(k), sn, ea.pc);
+      return dec ? (z <= ea.z_max) : (z >= ea.z_min);
+    };
+    auto fallen = [&](uint32_t k) {
+      const float z = simple_z32(key_to_float(k), sn, ea.pc);
+      return !(dec ? (z >= ea.z_min) : (z <= ea.z_max));
+    };
+    if (rising(kmax) && !fallen(kmin)) {
+      const uint32_t a = warp_first_true(kmin, kmax, rising);
+      // first key in [kmin, kmax] that has fallen, or kmax + 1 if none
+      const uint32_t f = fallen(kmax) ? warp_first_true(kmin, kmax, fallen) : kmax + 1u;
+      if (f > a) { lo_f = key_to_float(a); hi_f = key_to_float(f - 1u); }
+    }
+  }
+  if (threadIdx.x == 0) {
+    fs->mask_mode = by_depth ? 1 : 0;
+    fs->mask_lo = lo_f;
+    fs->mask_hi = hi_f;
   }
 }
 
