@@ -30,6 +30,9 @@
  *   a9 back-projection (:228-237), a10 colour gather (:239-244),
  *   a11 emission (:246), ax-1 depth-range mask + compaction   -> d2pc_emit_enqueue
  *   ax-2 voxel-grid down-sampling (north-star extension)      -> d2pc_voxel_enqueue
+ *   f3 preview stride (:495-506), save_xyz/las/ply (:329-389) -> d2pc_preview_rows_enqueue,
+ *                                                               d2pc_xyz_text_*, d2pc_las_records_enqueue,
+ *                                                               d2pc_ply_records_enqueue
  */
 #ifndef D2PC_H_
 #define D2PC_H_
@@ -186,6 +189,47 @@ int d2pc_voxel_enqueue(const D2pcConfig *cfg, double voxel_size, const float *d_
                        void *d_table, size_t table_bytes, float *d_vox_xyz, float *d_vox_rgb,
                        int32_t *d_vox_idx, uint32_t *d_vox_count, int32_t *d_vox_error,
                        void *stream);
+
+/* f3 -- byte layouts of the reference's writers and preview (backend/app.py:310-389, 495-506), produced on
+ * the device from ONE frame's emitted rows (d_xyz / d_rgb point at that frame's slot, d_count at its row
+ * count; capacity_rows = N bounds the launch).  Headers and file I/O stay on the host.
+ *
+ * preview rows (app.py:495-500): points[::stride], stride = max(1, n // max_preview) when n > max_preview.
+ *   d_out_xyz/rgb float32 [out_capacity_rows, 3] (2 * max_preview rows always suffice); d_out_count uint32 [1] */
+int d2pc_preview_rows_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count,
+                              uint32_t max_preview, float *d_out_xyz, float *d_out_rgb,
+                              uint32_t out_capacity_rows, uint32_t *d_out_count, void *stream);
+
+/* XYZ ASCII (save_xyz, app.py:379-389): one line f"{x:.6f} {y:.6f} {z:.6f} {int(r)} {int(g)} {int(b)}\n" per
+ * row, byte-identical to Python's formatting of numpy.float32 values.  Two steps because the size is data
+ * dependent: measure (per-tile byte counts + scan -> *d_text_bytes, *d_error = 1 if a value cannot be
+ * formatted: |coordinate| >= 2^44, non-finite colour), then write into a buffer of at least that size. */
+int d2pc_xyz_text_scratch_bytes(uint32_t capacity_rows, size_t *bytes);
+int d2pc_xyz_text_measure_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count,
+                                  uint32_t capacity_rows, void *d_scratch, size_t scratch_bytes,
+                                  unsigned long long *d_text_bytes, int32_t *d_error, void *stream);
+int d2pc_xyz_text_write_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count,
+                                uint32_t capacity_rows, const void *d_scratch, size_t scratch_bytes,
+                                const unsigned long long *d_text_bytes, const int32_t *d_error, char *d_text,
+                                size_t text_capacity, void *stream);
+
+/* min x, y, z of the rows (float(points[:, k].min()), app.py:352) for callers that did not ask emit for its
+ * fused bounds: d_scratch3 uint32 [3], d_min3 float32 [3] (first half of a d_bounds block). */
+int d2pc_rows_min_enqueue(const float *d_xyz, const uint32_t *d_count, uint32_t capacity_rows,
+                          uint32_t *d_scratch3, float *d_min3, void *stream);
+
+/* LAS 1.2 point format 2 records (save_las, app.py:343-377), 26 bytes each: X/Y/Z = int32(np.round((x -
+ * offset) / scale)) with offset = the frame's min x/y/z (d_bounds of emit, want_bounds = 1), colours
+ * uint16(clip(c, 0, 255)) * 256, all other fields 0.  d_int_minmax int32 [6] = min X,Y,Z, max X,Y,Z (for the
+ * header); *d_error = 1 if a scaled coordinate leaves int32.  d_records must be 16-byte aligned. */
+int d2pc_las_records_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count,
+                             uint32_t capacity_rows, const float *d_bounds, double scale, uint8_t *d_records,
+                             int32_t *d_int_minmax, int32_t *d_error, void *stream);
+
+/* Binary little-endian PLY vertices as Open3D writes them (save_ply, app.py:329-341), 27 bytes each:
+ * float64 x, y, z; uchar red, green, blue = round(clamp(float32(c / 255), 0, 1) * 255). */
+int d2pc_ply_records_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count,
+                             uint32_t capacity_rows, uint8_t *d_records, void *stream);
 
 #ifdef __cplusplus
 }

@@ -499,6 +499,79 @@ def voxel_downsample(points: np.ndarray, colors: np.ndarray, voxel_size: float):
 # --------------------------------------------------------------------------------------------
 # comparison helpers
 # --------------------------------------------------------------------------------------------
+
+# --------------------------------------------------------------------------------------------
+# f3  writer byte layouts and preview rows (backend/app.py:310-389, 495-506)
+# --------------------------------------------------------------------------------------------
+def preview_rows(points: np.ndarray, colors: np.ndarray, max_preview: int = 20000):
+    """app.py:495-503: the strided rows that become the preview JSON (before ``.astype(float).tolist()``)."""
+    if len(points) > max_preview:
+        stride = max(1, len(points) // max_preview)
+        pprev = points[::stride]
+        cprev = colors[::stride] if colors is not None and len(colors) else np.zeros_like(pprev)
+    else:
+        pprev = points
+        cprev = colors if colors is not None and len(colors) else np.zeros_like(points)
+    return pprev, cprev
+
+
+def xyz_text(points: np.ndarray, colors: np.ndarray) -> bytes:
+    """The bytes save_xyz writes (app.py:383-387): the same f-string over the same numpy scalars."""
+    lines = []
+    for i in range(len(points)):
+        x, y, z = points[i]
+        r, g, b = colors[i] if len(colors) > 0 else [128, 128, 128]
+        lines.append(f"{x:.6f} {y:.6f} {z:.6f} {int(r)} {int(g)} {int(b)}\n")
+    return "".join(lines).encode("ascii")
+
+
+LAS_RECORD_DTYPE = np.dtype([("X", "<i4"), ("Y", "<i4"), ("Z", "<i4"), ("intensity", "<u2"), ("bit_fields", "u1"),
+                             ("classification", "u1"), ("scan_angle_rank", "i1"), ("user_data", "u1"),
+                             ("point_source_id", "<u2"), ("red", "<u2"), ("green", "<u2"), ("blue", "<u2")])
+
+
+def las_records(points: np.ndarray, colors: np.ndarray, scale: float = 0.01):
+    """save_las (app.py:343-377) up to the point records: LAS 1.2 point format 2 (26 bytes).
+    PARITY UNPINNED: laspy is not installed in the build container; this restates laspy 2.x's
+    ``ScaledArrayView`` assignment, ``np.round((value - offset) / scale)`` cast to int32, from its
+    published source.  Returns (records, offsets[3])."""
+    assert LAS_RECORD_DTYPE.itemsize == 26
+    offset = [float(points[:, 0].min()), float(points[:, 1].min()), float(points[:, 2].min())]
+    rec = np.zeros(len(points), dtype=LAS_RECORD_DTYPE)
+    for k, name in enumerate("XYZ"):
+        # laspy keeps scale / offset as float64 arrays (header.scales / header.offsets), so the float32
+        # coordinates are promoted and the arithmetic is float64
+        q = np.round((np.array(points[:, k]) - np.float64(offset[k])) / np.float64(scale))
+        if q.max() > np.iinfo(np.int32).max or q.min() < np.iinfo(np.int32).min:
+            raise OverflowError("scaled coordinate out of int32 range")
+        rec[name] = q.astype(np.int32)
+    c = np.clip(colors, 0, 255).astype(np.uint16)
+    rec["red"], rec["green"], rec["blue"] = c[:, 0] * 256, c[:, 1] * 256, c[:, 2] * 256
+    return rec, offset
+
+
+PLY_RECORD_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+
+
+def ply_records(points: np.ndarray, colors: np.ndarray) -> np.ndarray:
+    """save_ply (app.py:329-341): the vertex records of Open3D's binary little-endian PLY.
+    PARITY UNPINNED: Open3D is not installed here; restated from its published writer
+    (``double x,y,z; uchar red,green,blue``, colour = round(clamp(c, 0, 1) * 255) of the float64 copy of
+    ``colors / 255.0``, which NumPy evaluates in float32)."""
+    assert PLY_RECORD_DTYPE.itemsize == 27
+    rec = np.zeros(len(points), dtype=PLY_RECORD_DTYPE)
+    rec["x"], rec["y"], rec["z"] = points[:, 0], points[:, 1], points[:, 2]
+    c = (colors / 255.0).astype(np.float64)
+    c8 = np.floor(np.clip(c, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
+    rec["red"], rec["green"], rec["blue"] = c8[:, 0], c8[:, 1], c8[:, 2]
+    return rec
+
+
+PLY_HEADER = ("ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\nelement vertex {n}\n"
+              "property double x\nproperty double y\nproperty double z\n"
+              "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
+
+
 def bit_equal(a: np.ndarray, b: np.ndarray) -> bool:
     a = np.ascontiguousarray(a)
     b = np.ascontiguousarray(b)

@@ -62,3 +62,22 @@ def build_case(spec):
     H, W, s = spec["img"]
     h, w, ds, kind = spec["depth"]
     return make_image(H, W, s), make_depth(h, w, ds, kind), dict(spec["kw"])
+
+
+def writer_rows(seed: int = 7, n: int = 4000):
+    """Rows that stress the writers' formatting (row f3): decimal ties (odd j / 128 has a 7th decimal of
+    exactly 5), values that round to +-0.000000, signed zeros, large and tiny magnitudes, denormals."""
+    rng = np.random.default_rng(seed)
+    p = (rng.standard_normal((n, 3)) * 10).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-9, -1e-9, 4.9e-7, 5.1e-7, -5e-7, 1 / 128, 3 / 128, -5 / 128, 7 / 256, 0.5, -0.5,
+                        1.0, -1.0, 9.9999995, 123456.789, -98765.4321, 1e7, 16777216.0, 3.0e12, 2.0 ** 43,
+                        1e-38, 1e-45, -1e-45, 0.1, 0.2, 0.3, 2.675, 1.0000005, 0.9999995, 999999.5],
+                       dtype=np.float32)
+    k = len(special)
+    p[:k, 0] = special
+    p[:k, 1] = special[::-1]
+    p[:k, 2] = np.roll(special, 5)
+    p[k:2 * k, :] = (np.arange(k * 3, dtype=np.float32).reshape(k, 3) * 2 + 1) / 128   # more exact ties
+    c = rng.integers(0, 256, (n, 3)).astype(np.float32)
+    c[:4] = [[0, 0, 0], [255, 255, 255], [128, 128, 128], [1, 254, 17]]
+    return p, c

@@ -9,11 +9,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_build", "libd2pc_hostmath.so")
 SRC = os.path.join(HERE, "hostmath.cpp")
 HDR = os.path.join(HERE, "..", "..", "image_to_pointcloud_b200", "csrc", "d2pc_math.h")
+HDR2 = os.path.join(HERE, "..", "..", "image_to_pointcloud_b200", "csrc", "d2pc_format.h")
 
 
 def build(force=False):
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    newest = max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+    newest = max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2))
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17",
                         SRC, "-o", SO], check=True)
@@ -32,6 +33,12 @@ def load():
     lib.hm_mask_check.restype = C.c_long
     lib.hm_mask_check.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_float, C.c_float,
                                   C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+    lib.hm_xyz_text.restype = C.c_long
+    lib.hm_xyz_text.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+    lib.hm_las_records.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_double, C.c_void_p]
+    lib.hm_ply_records.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+    lib.hm_preview_stride.restype = C.c_uint
+    lib.hm_preview_stride.argtypes = [C.c_uint, C.c_uint]
     return lib
 
 

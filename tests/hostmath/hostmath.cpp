@@ -166,3 +166,32 @@ long hm_div_check(long n, unsigned long seed, int mode) {
 }
 
 }  // extern "C"
+
+// ---- f3: writer byte layouts (csrc/d2pc_format.h) ----------------------------------------------
+#include "../../image_to_pointcloud_b200/csrc/d2pc_format.h"
+extern "C" {
+// all lines of save_xyz into out (capacity cap); returns total bytes, -1 on a formatting error, -2 if cap is too small
+long hm_xyz_text(const float *xyz, const float *rgb, long n, char *out, long cap) {
+  long pos = 0;
+  char line[d2pc::kXyzMaxLine];
+  for (long i = 0; i < n; ++i) {
+    int m = d2pc::format_xyz_line(xyz + 3 * i, rgb + 3 * i, line);
+    if (m < 0) return -1;
+    if (pos + m > cap) return -2;
+    memcpy(out + pos, line, m);
+    pos += m;
+  }
+  return pos;
+}
+int hm_las_records(const float *xyz, const float *rgb, long n, const double *off, double scale, unsigned char *out) {
+  int ok = 1;
+  int32_t q[3];
+  for (long i = 0; i < n; ++i)
+    if (!d2pc::las_record(xyz + 3 * i, rgb + 3 * i, off, scale, out + 26 * i, q)) ok = 0;
+  return ok;
+}
+void hm_ply_records(const float *xyz, const float *rgb, long n, unsigned char *out) {
+  for (long i = 0; i < n; ++i) d2pc::ply_record(xyz + 3 * i, rgb + 3 * i, out + 27 * i);
+}
+unsigned hm_preview_stride(unsigned n, unsigned max_preview) { return d2pc::preview_stride(n, max_preview); }
+}
