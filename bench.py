@@ -433,6 +433,29 @@ def run_extras(m, device):
     # BASELINE configs[2] / [4]: 4K frame, depth-range mask, voxel-size sweep (voxel stage alone)
     from profiles.voxel_sweep import sweep
     out["4k_zrange_voxel_sweep"] = sweep(iters=5, peak=measured_peak()[0])
+    # row f3: writer byte layouts on one 1080p cloud (kernels only)
+    from profiles.writers_bench import bench as writers_bench
+    out["writers_1080p"] = writers_bench()
+    # the drop-in call itself: NumPy in, NumPy out, one image (what backend/app.py:468 does per request)
+    import numpy as np
+    rng = np.random.default_rng(1)
+    lat = {}
+    for name, (H, W, h, w, dens) in {"480p_dav2_medium (UI default)": (480, 640, 518, 686, "medium"),
+                                     "1080p_dav2_high": (1080, 1920, 518, 924, "high"),
+                                     "1080p_native_high": (1080, 1920, 1080, 1920, "high"),
+                                     "4k_dav2_high": (2160, 3840, 518, 924, "high")}.items():
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        dep = (rng.random((h, w)) * 20).astype(np.float32)
+        for _ in range(3):
+            p, c = m.depth_to_point_cloud(img, dep, density=dens, device=device)
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            p, c = m.depth_to_point_cloud(img, dep, density=dens, device=device)
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        lat[name] = {"points": len(p), "median_ms": round(ts[5] * 1e3, 3), "mpoints_per_s": round(len(p) / ts[5] / 1e6, 1)}
+    out["single_call_latency_numpy_in_out"] = lat
     return out
 
 
