@@ -18,7 +18,7 @@ EXPORTS = [
     "d2pc_emit_enqueue", "d2pc_smooth_scratch_bytes", "d2pc_emit_smooth_enqueue",
     "d2pc_preview_enqueue", "d2pc_voxel_table_bytes", "d2pc_voxel_table_init", "d2pc_voxel_enqueue",
     "d2pc_preview_rows_enqueue", "d2pc_xyz_text_scratch_bytes", "d2pc_xyz_text_measure_enqueue",
-    "d2pc_xyz_text_write_enqueue", "d2pc_rows_min_enqueue", "d2pc_las_records_enqueue", "d2pc_ply_records_enqueue",
+    "d2pc_xyz_text_write_enqueue", "d2pc_rows_bounds_enqueue", "d2pc_las_records_enqueue", "d2pc_ply_records_enqueue", "d2pc_sor_scratch_bytes", "d2pc_sor_enqueue",
 ]
 
 
@@ -87,9 +87,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.d2pc_xyz_text_scratch_bytes.argtypes = [C.c_uint32, C.POINTER(C.c_size_t)]
     lib.d2pc_xyz_text_measure_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp, vp]
     lib.d2pc_xyz_text_write_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp]
-    lib.d2pc_rows_min_enqueue.argtypes = [vp, vp, C.c_uint32, vp, vp, vp]
+    lib.d2pc_rows_bounds_enqueue.argtypes = [vp, vp, C.c_uint32, vp, vp, vp]
     lib.d2pc_las_records_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_double, vp, vp, vp, vp]
     lib.d2pc_ply_records_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, vp]
+    lib.d2pc_sor_scratch_bytes.argtypes = [C.c_uint32, C.POINTER(C.c_size_t)]
+    lib.d2pc_sor_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_int32, C.c_double, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("d2pc_error_string", "d2pc_last_cuda_error"):

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libd2pc.so")
-SOURCES = ["d2pc_api.cu", "d2pc_stats.cu", "d2pc_emit.cu", "d2pc_voxel.cu", "d2pc_serialise.cu"]
+SOURCES = ["d2pc_api.cu", "d2pc_stats.cu", "d2pc_emit.cu", "d2pc_voxel.cu", "d2pc_serialise.cu", "d2pc_sor.cu"]
 HEADERS = ["d2pc_math.h", "d2pc_format.h", "d2pc_device.cuh", os.path.join("..", "..", "include", "d2pc.h")]
 
 NVCC_FLAGS = [

@@ -190,33 +190,42 @@ __global__ void __launch_bounds__(kSerThreads) ser_ply_kernel(const float *xyz, 
   });
 }
 
-// per-axis minimum of the rows (float(points[:, k].min()), app.py:352) when emit's fused bounds are not at hand
-__global__ void ser_min_init_kernel(uint32_t *keys) {
-  if (threadIdx.x < 3) keys[threadIdx.x] = 0xFFFFFFFFu;
+// per-axis min / max of the rows (float(points[:, k].min()), app.py:352, 394-399) when emit's fused bounds
+// are not at hand: keys[0..2] = min, keys[3..5] = max (ordered uint32 keys)
+__global__ void ser_bounds_init_kernel(uint32_t *keys) {
+  if (threadIdx.x < 6) keys[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
 }
-__global__ void __launch_bounds__(kSerThreads) ser_min_kernel(const float *xyz, const uint32_t *count, uint32_t *keys) {
-  __shared__ uint32_t s_k[3];
-  if (threadIdx.x < 3) s_k[threadIdx.x] = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(kSerThreads) ser_bounds_kernel(const float *xyz, const uint32_t *count, uint32_t *keys) {
+  __shared__ uint32_t s_k[6];
+  if (threadIdx.x < 6) s_k[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
   __syncthreads();
   const uint32_t n = *count;
-  uint32_t k3[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float v = __ldg(xyz + 3 * (size_t)i + k);
-      if (v == v) k3[k] = min(k3[k], float_to_key(v));  // NaN would poison numpy's min; callers never pass it
+      if (v == v) {  // NaN would poison numpy's min / max; callers never pass it
+        const uint32_t key = float_to_key(v);
+        lo[k] = min(lo[k], key);
+        hi[k] = max(hi[k], key);
+      }
     }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const uint32_t m = warp_min(k3[k]);
-    if ((threadIdx.x & 31) == 0) atomicMin(&s_k[k], m);
+    const uint32_t a = warp_min(lo[k]), b = warp_max(hi[k]);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_k[k], a); atomicMax(&s_k[3 + k], b); }
   }
   __syncthreads();
   if (threadIdx.x < 3) atomicMin(&keys[threadIdx.x], s_k[threadIdx.x]);
+  else if (threadIdx.x < 6) atomicMax(&keys[threadIdx.x], s_k[threadIdx.x]);
 }
-__global__ void ser_min_export_kernel(const uint32_t *keys, float *out) {
-  if (threadIdx.x < 3) out[threadIdx.x] = keys[threadIdx.x] == 0xFFFFFFFFu ? nan_f32() : key_to_float(keys[threadIdx.x]);
+__global__ void ser_bounds_export_kernel(const uint32_t *keys, float *out) {
+  if (threadIdx.x < 6) {
+    const bool empty = keys[0] == 0xFFFFFFFFu && keys[3] == 0u;
+    out[threadIdx.x] = empty ? nan_f32() : key_to_float(keys[threadIdx.x]);
+  }
 }
 
 __global__ void ser_las_init_kernel(int32_t *int_minmax, int32_t *err) {
@@ -279,15 +288,15 @@ extern "C" int d2pc_xyz_text_write_enqueue(const float *d_xyz, const float *d_rg
   return D2PC_OK;
 }
 
-extern "C" int d2pc_rows_min_enqueue(const float *d_xyz, const uint32_t *d_count, uint32_t capacity_rows,
-                                     uint32_t *d_scratch3, float *d_min3, void *stream) {
-  if (!d_xyz || !d_count || !d_scratch3 || !d_min3 || capacity_rows == 0) return D2PC_ERR_INVALID_ARGUMENT;
+extern "C" int d2pc_rows_bounds_enqueue(const float *d_xyz, const uint32_t *d_count, uint32_t capacity_rows,
+                                        uint32_t *d_scratch6, float *d_bounds6, void *stream) {
+  if (!d_xyz || !d_count || !d_scratch6 || !d_bounds6 || capacity_rows == 0) return D2PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
-  ser_min_init_kernel<<<1, 32, 0, st>>>(d_scratch3);
+  ser_bounds_init_kernel<<<1, 32, 0, st>>>(d_scratch6);
   D2PC_CHECK_LAUNCH();
-  ser_min_kernel<<<min(ser_tiles(capacity_rows), 148u * 8u), kSerThreads, 0, st>>>(d_xyz, d_count, d_scratch3);
+  ser_bounds_kernel<<<min(ser_tiles(capacity_rows), 148u * 8u), kSerThreads, 0, st>>>(d_xyz, d_count, d_scratch6);
   D2PC_CHECK_LAUNCH();
-  ser_min_export_kernel<<<1, 32, 0, st>>>(d_scratch3, d_min3);
+  ser_bounds_export_kernel<<<1, 32, 0, st>>>(d_scratch6, d_bounds6);
   D2PC_CHECK_LAUNCH();
   return D2PC_OK;
 }

@@ -1,0 +1,421 @@
+// d2pc_sor.cu -- row f1: statistical outlier removal, the step the reference runs right after the
+// hot path (refine_point_cloud, backend/app.py:252-269 -> Open3D remove_statistical_outlier(
+// nb_neighbors=20, std_ratio=2.0)).  Spec (Open3D geometry/PointCloud.cpp, restated in
+// oracle/d2pc_oracle.py::statistical_outlier_removal; Open3D itself is not installed: parity unpinned):
+//   avg[i]  = mean of sqrt(d2) over the k nearest points of i INCLUDING i itself, d2 accumulated
+//             axis by axis in float64, summed in ascending order
+//   mean    = sum(avg[avg > 0]) / N ;  std = sqrt(sum((avg - mean)^2 [avg > 0]) / (N - 1))
+//   keep i  iff 0 < avg[i] < mean + std_ratio * std          (rows keep their order)
+//
+// Exact k-NN on the device with a uniform grid over the cloud's bounding box:
+//   begin    cell size h such that the grid has at most kSorCells cells (one thread)
+//   count    cell of every point, per-cell counts (atomics)
+//   scan     exclusive prefix over the cells (block scan, scan of block sums, add)
+//   scatter  points copied into cell order (float32 x, y, z)
+//   query    one thread per point: own cell, then shells of growing Chebyshev radius R; the sorted
+//            list of the k smallest d2 lives in local memory; the search stops as soon as the k-th
+//            distance is no larger than the distance to the unvisited region (R*h + distance to the
+//            own cell's nearest face), which makes the result exact, not approximate
+//   stats    deterministic two-pass reduction by one CTA -> threshold
+//   compact  per-tile kept counts, scan, ordered copy of kept rows + their source indices
+#include "d2pc_device.cuh"
+
+namespace d2pc {
+
+constexpr uint32_t kSorCells = 1u << 22;  // grid cells (dense arrays): 4 M
+constexpr int kSorMaxK = 64;
+constexpr int kSorThreads = 256;
+constexpr int kSorScanThreads = 1024;
+
+struct __align__(256) SorHeader {
+  double mn[3];
+  double h, slack;
+  int32_t dim[3];
+  uint32_t ncells, n;
+  double cloud_mean, std_dev, thr;
+  double sum1, sum2;
+};
+
+struct SorWs {
+  SorHeader *hdr;
+  uint32_t *cell_off;   // [kSorCells + 1]
+  uint32_t *cell_cnt;   // [kSorCells]  counts, then scatter cursors
+  uint32_t *blk_sum;    // [kSorCells / 1024 + 1]
+  uint32_t *pt_cell;    // [N]
+  float *sorted;        // [N][3]
+  double *avg;          // [N]
+  uint32_t *tile_cnt;   // [N / 256 + 1]
+};
+
+inline size_t sor_ws_bytes(uint32_t n_rows) {
+  size_t b = sizeof(SorHeader);
+  b += align_up((size_t)(kSorCells + 1) * 4, 256) + align_up((size_t)kSorCells * 4, 256);
+  b += align_up((size_t)(kSorCells / kSorScanThreads + 1) * 4, 256);
+  b += align_up((size_t)n_rows * 4, 256) + align_up((size_t)n_rows * 12, 256) + align_up((size_t)n_rows * 8, 256);
+  b += align_up((size_t)(n_rows / kSorThreads + 1) * 4, 256);
+  return b;
+}
+inline SorWs sor_ws(void *base, uint32_t n_rows) {
+  SorWs w;
+  char *p = (char *)base;
+  w.hdr = (SorHeader *)p;      p += sizeof(SorHeader);
+  w.cell_off = (uint32_t *)p;  p += align_up((size_t)(kSorCells + 1) * 4, 256);
+  w.cell_cnt = (uint32_t *)p;  p += align_up((size_t)kSorCells * 4, 256);
+  w.blk_sum = (uint32_t *)p;   p += align_up((size_t)(kSorCells / kSorScanThreads + 1) * 4, 256);
+  w.pt_cell = (uint32_t *)p;   p += align_up((size_t)n_rows * 4, 256);
+  w.sorted = (float *)p;       p += align_up((size_t)n_rows * 12, 256);
+  w.avg = (double *)p;         p += align_up((size_t)n_rows * 8, 256);
+  w.tile_cnt = (uint32_t *)p;
+  return w;
+}
+
+__global__ void sor_begin_kernel(SorWs w, const uint32_t *count, const float *bounds) {
+  if (threadIdx.x != 0) return;
+  SorHeader *h = w.hdr;
+  const uint32_t n = *count;
+  h->n = n;
+  double ext[3], mx = 0.0;
+  for (int a = 0; a < 3; ++a) {
+    const double lo = (double)bounds[a], hi = (double)bounds[3 + a];
+    h->mn[a] = (n > 0 && lo == lo) ? lo : 0.0;
+    ext[a] = (n > 0 && hi == hi && lo == lo && hi > lo) ? hi - lo : 0.0;
+    if (ext[a] > mx) mx = ext[a];
+  }
+  // about two cells per point (most stay empty for surface-like clouds), never more than kSorCells
+  double cap = 2.0 * (double)n;
+  cap = cap < 64.0 ? 64.0 : (cap > (double)kSorCells ? (double)kSorCells : cap);
+  double cs = mx > 0.0 ? mx / 1048576.0 : 1.0;
+  int32_t d[3];
+  while (true) {
+    double prod = 1.0;
+    for (int a = 0; a < 3; ++a) {
+      const double q = floor(ext[a] / cs) + 1.0;
+      d[a] = q < 2.0e9 ? (int32_t)q : 2000000000;
+      prod *= (double)d[a];
+    }
+    if (prod <= cap) break;
+    cs *= 1.125;
+  }
+  h->h = cs;
+  h->slack = 1e-9 * mx + 1e-300;
+  h->dim[0] = d[0]; h->dim[1] = d[1]; h->dim[2] = d[2];
+  h->ncells = (uint32_t)d[0] * (uint32_t)d[1] * (uint32_t)d[2];
+}
+
+__device__ __forceinline__ void sor_cell_coords(const SorHeader *h, double x, double y, double z, int32_t c[3]) {
+  const double p[3] = {x, y, z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double q = floor((p[a] - h->mn[a]) / h->h);
+    int32_t i = q > 0.0 ? (q < 2.0e9 ? (int32_t)q : 2000000000) : 0;  // NaN -> 0
+    c[a] = min(i, h->dim[a] - 1);
+  }
+}
+
+__global__ void __launch_bounds__(kSorThreads) sor_count_kernel(SorWs w, const float *xyz) {
+  const SorHeader *h = w.hdr;
+  const uint32_t n = h->n;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int32_t c[3];
+    sor_cell_coords(h, (double)__ldg(xyz + 3 * (size_t)i), (double)__ldg(xyz + 3 * (size_t)i + 1),
+                    (double)__ldg(xyz + 3 * (size_t)i + 2), c);
+    const uint32_t cell = ((uint32_t)c[0] * (uint32_t)h->dim[1] + (uint32_t)c[1]) * (uint32_t)h->dim[2] + (uint32_t)c[2];
+    w.pt_cell[i] = cell;
+    atomicAdd(&w.cell_cnt[cell], 1u);
+  }
+}
+
+// block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp, uint32_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0, t = 0;
+  for (int k = 0; k < nw; ++k) { const uint32_t x = s_warp[k]; if (k < warp) woff += x; t += x; }
+  *total = t;
+  __syncthreads();
+  return woff + incl - v;
+}
+
+// phase 1: per block of 1024 cells, exclusive prefix inside the block -> cell_off, block total -> blk_sum;
+// the counts are zeroed so that the array can serve as the scatter cursors
+__global__ void __launch_bounds__(kSorScanThreads) sor_scan1_kernel(SorWs w) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t nc = w.hdr->ncells;
+  const uint32_t i = blockIdx.x * (uint32_t)kSorScanThreads + threadIdx.x;
+  if (blockIdx.x * (uint32_t)kSorScanThreads >= nc) return;
+  const uint32_t v = i < nc ? w.cell_cnt[i] : 0u;
+  uint32_t total;
+  const uint32_t ex = block_excl_scan(v, s_warp, &total);
+  if (i < nc) { w.cell_off[i] = ex; w.cell_cnt[i] = 0u; }
+  if (threadIdx.x == 0) w.blk_sum[blockIdx.x] = total;
+}
+// phase 2: exclusive scan of the block sums by one CTA
+__global__ void __launch_bounds__(kSorScanThreads) sor_scan2_kernel(SorWs w) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t nb = (w.hdr->ncells + kSorScanThreads - 1) / kSorScanThreads;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += kSorScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? w.blk_sum[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(v, s_warp, &total);
+    if (i < nb) w.blk_sum[i] = s_carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+}
+// phase 3: add the block offsets; the entry past the last cell holds n
+__global__ void __launch_bounds__(kSorScanThreads) sor_scan3_kernel(SorWs w) {
+  const uint32_t nc = w.hdr->ncells;
+  const uint32_t i = blockIdx.x * (uint32_t)kSorScanThreads + threadIdx.x;
+  if (i < nc) w.cell_off[i] += w.blk_sum[blockIdx.x];
+  if (i == nc) w.cell_off[nc] = w.hdr->n;
+}
+
+__global__ void __launch_bounds__(kSorThreads) sor_scatter_kernel(SorWs w, const float *xyz) {
+  const uint32_t n = w.hdr->n;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t cell = w.pt_cell[i];
+    const uint32_t pos = w.cell_off[cell] + atomicAdd(&w.cell_cnt[cell], 1u);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w.sorted[3 * (size_t)pos + k] = __ldg(xyz + 3 * (size_t)i + k);
+  }
+}
+
+__device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, double qx, double qy, double qz,
+                                               double *best, int k) {
+  const uint32_t s = w.cell_off[cell], e = w.cell_off[cell + 1];
+  for (uint32_t j = s; j < e; ++j) {
+    const double dx = qx - (double)w.sorted[3 * (size_t)j], dy = qy - (double)w.sorted[3 * (size_t)j + 1],
+                 dz = qz - (double)w.sorted[3 * (size_t)j + 2];
+    double d2 = dx * dx;   // nanoflann L2_Simple: result += diff * diff, axis by axis (no contraction: --fmad=false)
+    d2 += dy * dy;
+    d2 += dz * dz;
+    if (d2 < best[k - 1]) {
+      int t = k - 1;
+      while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
+      best[t] = d2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const float *xyz, int nb_neighbors) {
+  const SorHeader *h = w.hdr;
+  const uint32_t n = h->n;
+  const uint32_t i = blockIdx.x * (uint32_t)kSorThreads + threadIdx.x;
+  if (i >= n) return;
+  const int k = (int)min((uint32_t)nb_neighbors, n);
+  double best[kSorMaxK];
+  for (int t = 0; t < k; ++t) best[t] = __longlong_as_double(0x7FF0000000000000ll);
+  const double q[3] = {(double)__ldg(xyz + 3 * (size_t)i), (double)__ldg(xyz + 3 * (size_t)i + 1),
+                       (double)__ldg(xyz + 3 * (size_t)i + 2)};
+  const int32_t nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
+  const uint32_t cell = w.pt_cell[i];
+  const int32_t c2 = (int32_t)(cell % (uint32_t)nz), c1 = (int32_t)((cell / (uint32_t)nz) % (uint32_t)ny),
+                c0 = (int32_t)(cell / ((uint32_t)nz * (uint32_t)ny));
+  const int32_t c[3] = {c0, c1, c2};
+  // distances from the query to the faces of its own cell (0 if rounding put it outside)
+  double dlo[3], dhi[3];
+  int32_t rmax = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double lo = h->mn[a] + (double)c[a] * h->h;
+    dlo[a] = fmax(q[a] - lo, 0.0);
+    dhi[a] = fmax(lo + h->h - q[a], 0.0);
+    rmax = max(rmax, max(c[a], h->dim[a] - 1 - c[a]));
+  }
+  sor_visit_cell(w, cell, q[0], q[1], q[2], best, k);
+  const int32_t dim[3] = {nx, ny, nz};
+  for (int32_t R = 1; R <= rmax; ++R) {
+    // Unvisited points lie beyond a face of the block of radius R - 1 that is still inside the grid:
+    // at least (R - 1) * h + (distance to the own cell's face on that side) away.
+    double reach = __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (c[a] - R >= 0) reach = fmin(reach, (double)(R - 1) * h->h + dlo[a]);
+      if (c[a] + R <= dim[a] - 1) reach = fmin(reach, (double)(R - 1) * h->h + dhi[a]);
+    }
+    reach -= h->slack;
+    if (reach > 0.0 && best[k - 1] <= reach * reach) break;
+    // shell of Chebyshev radius R, clipped to the grid, as six slabs (no cell is visited twice):
+    //   x faces: a0 = c0 -+ R, full (a1, a2) range;  y faces: a1 = c1 -+ R, a0 interior;  z faces: a0, a1 interior
+    const int32_t x0 = max(c0 - R, 0), x1 = min(c0 + R, nx - 1);
+    const int32_t y0 = max(c1 - R, 0), y1 = min(c1 + R, ny - 1);
+    const int32_t z0 = max(c2 - R, 0), z1 = min(c2 + R, nz - 1);
+    const int32_t xi0 = max(c0 - R + 1, 0), xi1 = min(c0 + R - 1, nx - 1);  // interior ranges
+    const int32_t yi0 = max(c1 - R + 1, 0), yi1 = min(c1 + R - 1, ny - 1);
+    for (int side = 0; side < 2; ++side) {
+      const int32_t a0 = side ? c0 + R : c0 - R;
+      if (a0 < 0 || a0 >= nx) continue;
+      for (int32_t a1 = y0; a1 <= y1; ++a1) {
+        const uint32_t row = ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz;
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q[0], q[1], q[2], best, k);
+      }
+    }
+    for (int side = 0; side < 2; ++side) {
+      const int32_t a1 = side ? c1 + R : c1 - R;
+      if (a1 < 0 || a1 >= ny) continue;
+      for (int32_t a0 = xi0; a0 <= xi1; ++a0) {
+        const uint32_t row = ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz;
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q[0], q[1], q[2], best, k);
+      }
+    }
+    for (int side = 0; side < 2; ++side) {
+      const int32_t a2 = side ? c2 + R : c2 - R;
+      if (a2 < 0 || a2 >= nz) continue;
+      for (int32_t a0 = xi0; a0 <= xi1; ++a0)
+        for (int32_t a1 = yi0; a1 <= yi1; ++a1)
+          sor_visit_cell(w, ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz + (uint32_t)a2, q[0], q[1], q[2],
+                         best, k);
+    }
+  }
+  double s = 0.0;
+  for (int t = 0; t < k; ++t) s += sqrt(best[t]);  // ascending order, like std::accumulate over nanoflann's result
+  w.avg[i] = s / (double)k;
+}
+
+// cloud mean, Bessel-corrected standard deviation and the threshold; one CTA, fixed summation order
+__global__ void __launch_bounds__(1024) sor_stats_kernel(SorWs w, double std_ratio, double *stats) {
+  __shared__ double s_red[1024];
+  SorHeader *h = w.hdr;
+  const uint32_t n = h->n;
+  const int tid = threadIdx.x;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double mean = h->cloud_mean;
+    double acc = 0.0;
+    for (uint32_t i = tid; i < n; i += 1024u) {
+      const double a = w.avg[i];
+      if (a > 0.0) acc += pass == 0 ? a : (a - mean) * (a - mean);
+    }
+    s_red[tid] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+      if (tid < s) s_red[tid] += s_red[tid + s];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (pass == 0) {
+        h->cloud_mean = n > 0 ? s_red[0] / (double)n : 0.0;
+      } else {
+        h->std_dev = sqrt(s_red[0] / ((double)n - 1.0));
+        h->thr = h->cloud_mean + std_ratio * h->std_dev;
+        if (stats) { stats[0] = h->cloud_mean; stats[1] = h->std_dev; stats[2] = h->thr; stats[3] = (double)n; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ bool sor_keep(const SorWs &w, uint32_t i) {
+  const double a = w.avg[i];
+  return a > 0.0 && a < w.hdr->thr;
+}
+
+__global__ void __launch_bounds__(kSorThreads) sor_keep_count_kernel(SorWs w) {
+  __shared__ uint32_t s_warp[kSorThreads / 32];
+  const uint32_t n = w.hdr->n;
+  if (blockIdx.x * (uint32_t)kSorThreads >= n) return;
+  const uint32_t i = blockIdx.x * (uint32_t)kSorThreads + threadIdx.x;
+  uint32_t total;
+  block_excl_scan((i < n && sor_keep(w, i)) ? 1u : 0u, s_warp, &total);
+  if (threadIdx.x == 0) w.tile_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kSorScanThreads) sor_tile_scan_kernel(SorWs w, uint32_t *out_count) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t nt = (w.hdr->n + kSorThreads - 1) / kSorThreads;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nt; base += kSorScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nt ? w.tile_cnt[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(v, s_warp, &total);
+    if (i < nt) w.tile_cnt[i] = s_carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_count = s_carry;
+}
+
+__global__ void __launch_bounds__(kSorThreads) sor_compact_kernel(SorWs w, const float *xyz, const float *rgb, float *oxyz,
+                                                                  float *orgb, uint32_t *oindex) {
+  __shared__ uint32_t s_warp[kSorThreads / 32];
+  const uint32_t n = w.hdr->n;
+  if (blockIdx.x * (uint32_t)kSorThreads >= n) return;
+  const uint32_t i = blockIdx.x * (uint32_t)kSorThreads + threadIdx.x;
+  const bool keep = i < n && sor_keep(w, i);
+  uint32_t total;
+  const uint32_t ex = block_excl_scan(keep ? 1u : 0u, s_warp, &total);
+  if (!keep) return;
+  const size_t dst = (size_t)w.tile_cnt[blockIdx.x] + ex;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    oxyz[3 * dst + k] = __ldg(xyz + 3 * (size_t)i + k);
+    if (orgb) orgb[3 * dst + k] = __ldg(rgb + 3 * (size_t)i + k);
+  }
+  if (oindex) oindex[dst] = i;
+}
+
+}  // namespace d2pc
+
+using namespace d2pc;
+
+extern "C" int d2pc_sor_scratch_bytes(uint32_t capacity_rows, size_t *bytes) {
+  if (!bytes || capacity_rows == 0) return D2PC_ERR_INVALID_ARGUMENT;
+  *bytes = sor_ws_bytes(capacity_rows);
+  return D2PC_OK;
+}
+
+extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count, uint32_t capacity_rows,
+                                const float *d_bounds, int32_t nb_neighbors, double std_ratio, void *d_scratch,
+                                size_t scratch_bytes, float *d_out_xyz, float *d_out_rgb, uint32_t *d_out_index,
+                                uint32_t *d_out_count, double *d_stats, void *stream) {
+  if (!d_xyz || !d_count || !d_bounds || !d_scratch || !d_out_xyz || !d_out_count) return D2PC_ERR_INVALID_ARGUMENT;
+  if ((d_out_rgb != nullptr) != (d_rgb != nullptr)) return D2PC_ERR_INVALID_ARGUMENT;
+  if (capacity_rows == 0 || nb_neighbors < 1 || nb_neighbors > kSorMaxK || !(std_ratio > 0.0)) return D2PC_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)d_scratch & 255u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
+  if (scratch_bytes < sor_ws_bytes(capacity_rows)) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t st = (cudaStream_t)stream;
+  SorWs w = sor_ws(d_scratch, capacity_rows);
+  cudaError_t e = cudaMemsetAsync(w.cell_cnt, 0, (size_t)kSorCells * 4, st);
+  if (e != cudaSuccess) return record_cuda_error(e);
+  const uint32_t row_blocks = (capacity_rows + kSorThreads - 1) / kSorThreads;
+  const uint32_t stride_blocks = min(row_blocks, 148u * 16u);
+  const uint32_t cell_blocks = kSorCells / kSorScanThreads + 1;
+  sor_begin_kernel<<<1, 32, 0, st>>>(w, d_count, d_bounds);
+  D2PC_CHECK_LAUNCH();
+  sor_count_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz);
+  D2PC_CHECK_LAUNCH();
+  sor_scan1_kernel<<<cell_blocks, kSorScanThreads, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_scan2_kernel<<<1, kSorScanThreads, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_scan3_kernel<<<cell_blocks, kSorScanThreads, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_scatter_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz);
+  D2PC_CHECK_LAUNCH();
+  sor_query_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, d_xyz, nb_neighbors);
+  D2PC_CHECK_LAUNCH();
+  sor_stats_kernel<<<1, 1024, 0, st>>>(w, std_ratio, d_stats);
+  D2PC_CHECK_LAUNCH();
+  sor_keep_count_kernel<<<row_blocks, kSorThreads, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_tile_scan_kernel<<<1, kSorScanThreads, 0, st>>>(w, d_out_count);
+  D2PC_CHECK_LAUNCH();
+  sor_compact_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, d_xyz, d_rgb, d_out_xyz, d_out_rgb, d_out_index);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}

@@ -141,9 +141,9 @@ def las_point_records(points, colors, scale: float = 0.01, offsets=None, device=
     with torch.cuda.device(dev):
         bounds = torch.zeros(6, dtype=torch.float32, device=dev)
         if offsets is None:  # float(points[:, k].min()), app.py:352
-            keys = torch.empty(3, dtype=torch.int32, device=dev)
-            check(lib.d2pc_rows_min_enqueue(xyz.data_ptr(), count.data_ptr(), n, keys.data_ptr(), bounds.data_ptr(),
-                                            _stream(dev)), "d2pc_rows_min_enqueue")
+            keys = torch.empty(6, dtype=torch.int32, device=dev)
+            check(lib.d2pc_rows_bounds_enqueue(xyz.data_ptr(), count.data_ptr(), n, keys.data_ptr(), bounds.data_ptr(),
+                                               _stream(dev)), "d2pc_rows_bounds_enqueue")
             offsets = [float(v) for v in bounds[:3].cpu()]
         else:
             bounds[:3] = torch.tensor([float(v) for v in offsets], dtype=torch.float32)

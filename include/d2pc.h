@@ -30,6 +30,7 @@
  *   a9 back-projection (:228-237), a10 colour gather (:239-244),
  *   a11 emission (:246), ax-1 depth-range mask + compaction   -> d2pc_emit_enqueue
  *   ax-2 voxel-grid down-sampling (north-star extension)      -> d2pc_voxel_enqueue
+ *   f1 refine_point_cloud (:252-269, Open3D SOR)               -> d2pc_sor_enqueue
  *   f3 preview stride (:495-506), save_xyz/las/ply (:329-389) -> d2pc_preview_rows_enqueue,
  *                                                               d2pc_xyz_text_*, d2pc_las_records_enqueue,
  *                                                               d2pc_ply_records_enqueue
@@ -213,10 +214,11 @@ int d2pc_xyz_text_write_enqueue(const float *d_xyz, const float *d_rgb, const ui
                                 const unsigned long long *d_text_bytes, const int32_t *d_error, char *d_text,
                                 size_t text_capacity, void *stream);
 
-/* min x, y, z of the rows (float(points[:, k].min()), app.py:352) for callers that did not ask emit for its
- * fused bounds: d_scratch3 uint32 [3], d_min3 float32 [3] (first half of a d_bounds block). */
-int d2pc_rows_min_enqueue(const float *d_xyz, const uint32_t *d_count, uint32_t capacity_rows,
-                          uint32_t *d_scratch3, float *d_min3, void *stream);
+/* min / max x, y, z of the rows (float(points[:, k].min()) ..., app.py:352, 394-399) for callers that did not
+ * ask emit for its fused bounds: d_scratch6 uint32 [6], d_bounds6 float32 [6] = min x,y,z, max x,y,z
+ * (the d_bounds layout of emit; NaN for an empty cloud). */
+int d2pc_rows_bounds_enqueue(const float *d_xyz, const uint32_t *d_count, uint32_t capacity_rows,
+                             uint32_t *d_scratch6, float *d_bounds6, void *stream);
 
 /* LAS 1.2 point format 2 records (save_las, app.py:343-377), 26 bytes each: X/Y/Z = int32(np.round((x -
  * offset) / scale)) with offset = the frame's min x/y/z (d_bounds of emit, want_bounds = 1), colours
@@ -230,6 +232,22 @@ int d2pc_las_records_enqueue(const float *d_xyz, const float *d_rgb, const uint3
  * float64 x, y, z; uchar red, green, blue = round(clamp(float32(c / 255), 0, 1) * 255). */
 int d2pc_ply_records_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count,
                              uint32_t capacity_rows, uint8_t *d_records, void *stream);
+
+/* f1 -- statistical outlier removal (refine_point_cloud, app.py:252-269: Open3D remove_statistical_outlier(
+ * nb_neighbors=20, std_ratio=2.0)) on ONE frame's rows: exact k-nearest neighbours (the point itself
+ * included, float64 distances) through a uniform grid, avg[i] = mean of the k distances, keep
+ * 0 < avg[i] < mean(avg) + std_ratio * std(avg) (Bessel-corrected, Open3D's definitions), kept rows in order.
+ *   d_bounds     float32 [6] min/max of the rows (emit want_bounds = 1, or d2pc_rows_bounds_enqueue)
+ *   d_scratch    d2pc_sor_scratch_bytes(capacity_rows) bytes, 256-byte aligned
+ *   d_out_xyz/rgb float32 [capacity_rows, 3] (d_rgb / d_out_rgb may both be NULL); d_out_index uint32
+ *                [capacity_rows] source row of every kept row, or NULL; d_out_count uint32 [1]
+ *   d_stats      float64 [4] = cloud mean, standard deviation, threshold, N; or NULL
+ *   nb_neighbors 1..64 */
+int d2pc_sor_scratch_bytes(uint32_t capacity_rows, size_t *bytes);
+int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const uint32_t *d_count, uint32_t capacity_rows,
+                     const float *d_bounds, int32_t nb_neighbors, double std_ratio, void *d_scratch,
+                     size_t scratch_bytes, float *d_out_xyz, float *d_out_rgb, uint32_t *d_out_index,
+                     uint32_t *d_out_count, double *d_stats, void *stream);
 
 #ifdef __cplusplus
 }

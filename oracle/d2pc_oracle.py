@@ -572,6 +572,38 @@ PLY_HEADER = ("ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\n
               "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
 
 
+
+# --------------------------------------------------------------------------------------------
+# f1  statistical outlier removal (refine_point_cloud, backend/app.py:252-269)
+# --------------------------------------------------------------------------------------------
+def statistical_outlier_removal(points: np.ndarray, nb_neighbors: int = 20, std_ratio: float = 2.0):
+    """Open3D ``PointCloud::RemoveStatisticalOutliers`` as called at app.py:262 (points as float64).
+    PARITY UNPINNED: Open3D is not installed in the build container; this restates its published source
+    (geometry/PointCloud.cpp): exact k-NN *including the query point itself* (nanoflann, squared
+    distances accumulated axis by axis in float64), mean of the square roots summed in ascending order,
+    ``cloud_mean`` / ``sq_sum`` over the points with mean > 0 but divided by the number of points that
+    found neighbours, Bessel-corrected standard deviation, keep ``0 < mean < cloud_mean + std_ratio * std``.
+    The k-NN distances come from scipy's cKDTree (exact, float64).
+    Returns (kept indices int64, avg_distances float64 [N], (cloud_mean, std_dev, threshold))."""
+    from scipy.spatial import cKDTree
+    p = np.ascontiguousarray(points, dtype=F64)
+    n = len(p)
+    if n == 0:
+        return np.zeros(0, np.int64), np.zeros(0, F64), (0.0, 0.0, 0.0)
+    k = min(int(nb_neighbors), n)
+    dist, _ = cKDTree(p).query(p, k=k)
+    dist = dist.reshape(n, k)
+    avg = np.cumsum(dist, axis=1)[:, -1] / k          # std::accumulate: sequential, ascending order
+    valid = n                                           # every point finds at least itself
+    pos = avg > 0
+    cloud_mean = float(np.cumsum(np.where(pos, avg, 0.0))[-1]) / valid
+    sq = np.where(pos, (avg - cloud_mean) * (avg - cloud_mean), 0.0)
+    std_dev = float(np.sqrt(np.cumsum(sq)[-1] / (valid - 1))) if valid > 1 else float("nan")
+    thr = cloud_mean + std_ratio * std_dev
+    keep = np.nonzero(pos & (avg < thr))[0].astype(np.int64)
+    return keep, avg, (cloud_mean, std_dev, thr)
+
+
 def bit_equal(a: np.ndarray, b: np.ndarray) -> bool:
     a = np.ascontiguousarray(a)
     b = np.ascontiguousarray(b)
