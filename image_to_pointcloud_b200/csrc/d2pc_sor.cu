@@ -22,7 +22,7 @@
 
 namespace d2pc {
 
-constexpr uint32_t kSorCells = 1u << 22;  // grid cells (dense arrays): 4 M
+constexpr uint32_t kSorCells = 1u << 24;  // grid cells (dense arrays): 16 M
 constexpr int kSorMaxK = 64;
 constexpr int kSorThreads = 256;
 constexpr int kSorScanThreads = 1024;
@@ -42,7 +42,8 @@ struct SorWs {
   uint32_t *cell_cnt;   // [kSorCells]  counts, then scatter cursors
   uint32_t *blk_sum;    // [kSorCells / 1024 + 1]
   uint32_t *pt_cell;    // [N]
-  float *sorted;        // [N][3]
+  float *sorted;        // [N][3]  points in cell order
+  uint32_t *sorted_idx; // [N]     source row of every sorted point
   double *avg;          // [N]
   uint32_t *tile_cnt;   // [N / 256 + 1]
 };
@@ -51,7 +52,7 @@ inline size_t sor_ws_bytes(uint32_t n_rows) {
   size_t b = sizeof(SorHeader);
   b += align_up((size_t)(kSorCells + 1) * 4, 256) + align_up((size_t)kSorCells * 4, 256);
   b += align_up((size_t)(kSorCells / kSorScanThreads + 1) * 4, 256);
-  b += align_up((size_t)n_rows * 4, 256) + align_up((size_t)n_rows * 12, 256) + align_up((size_t)n_rows * 8, 256);
+  b += 2 * align_up((size_t)n_rows * 4, 256) + align_up((size_t)n_rows * 12, 256) + align_up((size_t)n_rows * 8, 256);
   b += align_up((size_t)(n_rows / kSorThreads + 1) * 4, 256);
   return b;
 }
@@ -64,6 +65,7 @@ inline SorWs sor_ws(void *base, uint32_t n_rows) {
   w.blk_sum = (uint32_t *)p;   p += align_up((size_t)(kSorCells / kSorScanThreads + 1) * 4, 256);
   w.pt_cell = (uint32_t *)p;   p += align_up((size_t)n_rows * 4, 256);
   w.sorted = (float *)p;       p += align_up((size_t)n_rows * 12, 256);
+  w.sorted_idx = (uint32_t *)p; p += align_up((size_t)n_rows * 4, 256);
   w.avg = (double *)p;         p += align_up((size_t)n_rows * 8, 256);
   w.tile_cnt = (uint32_t *)p;
   return w;
@@ -81,8 +83,8 @@ __global__ void sor_begin_kernel(SorWs w, const uint32_t *count, const float *bo
     ext[a] = (n > 0 && hi == hi && lo == lo && hi > lo) ? hi - lo : 0.0;
     if (ext[a] > mx) mx = ext[a];
   }
-  // about two cells per point (most stay empty for surface-like clouds), never more than kSorCells
-  double cap = 2.0 * (double)n;
+  // about eight cells per point (most stay empty for surface-like clouds), never more than kSorCells
+  double cap = 8.0 * (double)n;
   cap = cap < 64.0 ? 64.0 : (cap > (double)kSorCells ? (double)kSorCells : cap);
   double cs = mx > 0.0 ? mx / 1048576.0 : 1.0;
   int32_t d[3];
@@ -189,36 +191,65 @@ __global__ void __launch_bounds__(kSorThreads) sor_scatter_kernel(SorWs w, const
     const uint32_t pos = w.cell_off[cell] + atomicAdd(&w.cell_cnt[cell], 1u);
 #pragma unroll
     for (int k = 0; k < 3; ++k) w.sorted[3 * (size_t)pos + k] = __ldg(xyz + 3 * (size_t)i + k);
+    w.sorted_idx[pos] = i;
   }
 }
 
-__device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, double qx, double qy, double qz,
-                                               double *best, int k) {
+// float32 upper bound of the current k-th squared distance (inf while fewer than k points were seen)
+__device__ __forceinline__ float sor_filter(double kth) {
+  return __double2float_ru(kth) * 1.000001f;
+}
+
+// Candidates of one cell.  A float32 estimate of the squared distance (relative error < 4e-7) rejects most
+// candidates for a sixth of the cost; whatever passes the (conservative) filter is evaluated exactly.
+__device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, const double q[3], const float qf[3],
+                                               double *best, int k, float &thrf) {
   const uint32_t s = w.cell_off[cell], e = w.cell_off[cell + 1];
-  for (uint32_t j = s; j < e; ++j) {
-    const double dx = qx - (double)w.sorted[3 * (size_t)j], dy = qy - (double)w.sorted[3 * (size_t)j + 1],
-                 dz = qz - (double)w.sorted[3 * (size_t)j + 2];
-    double d2 = dx * dx;   // nanoflann L2_Simple: result += diff * diff, axis by axis (no contraction: --fmad=false)
-    d2 += dy * dy;
-    d2 += dz * dz;
-    if (d2 < best[k - 1]) {
-      int t = k - 1;
-      while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
-      best[t] = d2;
+  constexpr int U = 4;  // candidates in flight per iteration (independent loads and float32 estimates)
+  for (uint32_t j0 = s; j0 < e; j0 += U) {
+    float p[U][3], d2f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t j = min(j0 + (uint32_t)u, e - 1u);  // the tail repeats the last candidate (harmless: not < kth twice)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) p[u][a] = w.sorted[3 * (size_t)j + a];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float fx = qf[0] - p[u][0], fy = qf[1] - p[u][1], fz = qf[2] - p[u][2];
+      d2f[u] = fx * fx + fy * fy + fz * fz;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j0 + (uint32_t)u >= e || d2f[u] > thrf) continue;
+      const double dx = q[0] - (double)p[u][0], dy = q[1] - (double)p[u][1], dz = q[2] - (double)p[u][2];
+      double d2 = dx * dx;   // nanoflann L2_Simple: result += diff * diff, axis by axis (no contraction: --fmad=false)
+      d2 += dy * dy;
+      d2 += dz * dz;
+      if (d2 < best[k - 1]) {
+        int t = k - 1;
+        while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
+        best[t] = d2;
+        thrf = sor_filter(best[k - 1]);
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const float *xyz, int nb_neighbors) {
+// Queries run in CELL order (thread j owns the j-th sorted point): the lanes of a warp then share their
+// query cell, walk the same candidate lists with the same trip counts and read the same addresses.
+__global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int nb_neighbors) {
   const SorHeader *h = w.hdr;
   const uint32_t n = h->n;
-  const uint32_t i = blockIdx.x * (uint32_t)kSorThreads + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t j = blockIdx.x * (uint32_t)kSorThreads + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t i = w.sorted_idx[j];
   const int k = (int)min((uint32_t)nb_neighbors, n);
   double best[kSorMaxK];
   for (int t = 0; t < k; ++t) best[t] = __longlong_as_double(0x7FF0000000000000ll);
-  const double q[3] = {(double)__ldg(xyz + 3 * (size_t)i), (double)__ldg(xyz + 3 * (size_t)i + 1),
-                       (double)__ldg(xyz + 3 * (size_t)i + 2)};
+  const float qf[3] = {w.sorted[3 * (size_t)j], w.sorted[3 * (size_t)j + 1], w.sorted[3 * (size_t)j + 2]};
+  const double q[3] = {(double)qf[0], (double)qf[1], (double)qf[2]};
+  float thrf = __int_as_float(0x7F800000);
   const int32_t nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
   const uint32_t cell = w.pt_cell[i];
   const int32_t c2 = (int32_t)(cell % (uint32_t)nz), c1 = (int32_t)((cell / (uint32_t)nz) % (uint32_t)ny),
@@ -234,7 +265,7 @@ __global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const f
     dhi[a] = fmax(lo + h->h - q[a], 0.0);
     rmax = max(rmax, max(c[a], h->dim[a] - 1 - c[a]));
   }
-  sor_visit_cell(w, cell, q[0], q[1], q[2], best, k);
+  sor_visit_cell(w, cell, q, qf, best, k, thrf);
   const int32_t dim[3] = {nx, ny, nz};
   for (int32_t R = 1; R <= rmax; ++R) {
     // Unvisited points lie beyond a face of the block of radius R - 1 that is still inside the grid:
@@ -259,7 +290,7 @@ __global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const f
       if (a0 < 0 || a0 >= nx) continue;
       for (int32_t a1 = y0; a1 <= y1; ++a1) {
         const uint32_t row = ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz;
-        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q[0], q[1], q[2], best, k);
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q, qf, best, k, thrf);
       }
     }
     for (int side = 0; side < 2; ++side) {
@@ -267,7 +298,7 @@ __global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const f
       if (a1 < 0 || a1 >= ny) continue;
       for (int32_t a0 = xi0; a0 <= xi1; ++a0) {
         const uint32_t row = ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz;
-        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q[0], q[1], q[2], best, k);
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q, qf, best, k, thrf);
       }
     }
     for (int side = 0; side < 2; ++side) {
@@ -275,8 +306,8 @@ __global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const f
       if (a2 < 0 || a2 >= nz) continue;
       for (int32_t a0 = xi0; a0 <= xi1; ++a0)
         for (int32_t a1 = yi0; a1 <= yi1; ++a1)
-          sor_visit_cell(w, ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz + (uint32_t)a2, q[0], q[1], q[2],
-                         best, k);
+          sor_visit_cell(w, ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz + (uint32_t)a2, q, qf, best, k,
+                         thrf);
     }
   }
   double s = 0.0;
@@ -284,35 +315,41 @@ __global__ void __launch_bounds__(kSorThreads) sor_query_kernel(SorWs w, const f
   w.avg[i] = s / (double)k;
 }
 
-// cloud mean, Bessel-corrected standard deviation and the threshold; one CTA, fixed summation order
-__global__ void __launch_bounds__(1024) sor_stats_kernel(SorWs w, double std_ratio, double *stats) {
+// cloud mean, Bessel-corrected standard deviation and the threshold.  Two passes (sum, then squared
+// deviations); each pass: kSorStatBlocks CTAs write one partial each (fixed assignment of rows to threads and
+// a fixed tree inside the CTA), then one thread adds the partials in order: deterministic.
+constexpr int kSorStatBlocks = 256;
+__global__ void __launch_bounds__(1024) sor_partial_kernel(SorWs w, int pass, double *partial) {
   __shared__ double s_red[1024];
-  SorHeader *h = w.hdr;
+  const SorHeader *h = w.hdr;
   const uint32_t n = h->n;
   const int tid = threadIdx.x;
-  for (int pass = 0; pass < 2; ++pass) {
-    const double mean = h->cloud_mean;
-    double acc = 0.0;
-    for (uint32_t i = tid; i < n; i += 1024u) {
-      const double a = w.avg[i];
-      if (a > 0.0) acc += pass == 0 ? a : (a - mean) * (a - mean);
-    }
-    s_red[tid] = acc;
+  const double mean = h->cloud_mean;
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * 1024u + tid; i < n; i += (uint32_t)kSorStatBlocks * 1024u) {
+    const double a = w.avg[i];
+    if (a > 0.0) acc += pass == 0 ? a : (a - mean) * (a - mean);
+  }
+  s_red[tid] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (tid < s) s_red[tid] += s_red[tid + s];
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-      if (tid < s) s_red[tid] += s_red[tid + s];
-      __syncthreads();
-    }
-    if (tid == 0) {
-      if (pass == 0) {
-        h->cloud_mean = n > 0 ? s_red[0] / (double)n : 0.0;
-      } else {
-        h->std_dev = sqrt(s_red[0] / ((double)n - 1.0));
-        h->thr = h->cloud_mean + std_ratio * h->std_dev;
-        if (stats) { stats[0] = h->cloud_mean; stats[1] = h->std_dev; stats[2] = h->thr; stats[3] = (double)n; }
-      }
-    }
-    __syncthreads();
+  }
+  if (tid == 0) partial[blockIdx.x] = s_red[0];
+}
+__global__ void sor_finish_kernel(SorWs w, int pass, const double *partial, double std_ratio, double *stats) {
+  if (threadIdx.x != 0) return;
+  SorHeader *h = w.hdr;
+  const uint32_t n = h->n;
+  double t = 0.0;
+  for (int b = 0; b < kSorStatBlocks; ++b) t += partial[b];
+  if (pass == 0) {
+    h->cloud_mean = n > 0 ? t / (double)n : 0.0;
+  } else {
+    h->std_dev = sqrt(t / ((double)n - 1.0));
+    h->thr = h->cloud_mean + std_ratio * h->std_dev;
+    if (stats) { stats[0] = h->cloud_mean; stats[1] = h->std_dev; stats[2] = h->thr; stats[3] = (double)n; }
   }
 }
 
@@ -407,10 +444,15 @@ extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const ui
   D2PC_CHECK_LAUNCH();
   sor_scatter_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz);
   D2PC_CHECK_LAUNCH();
-  sor_query_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, d_xyz, nb_neighbors);
+  sor_query_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, nb_neighbors);
   D2PC_CHECK_LAUNCH();
-  sor_stats_kernel<<<1, 1024, 0, st>>>(w, std_ratio, d_stats);
-  D2PC_CHECK_LAUNCH();
+  double *partial = reinterpret_cast<double *>(w.blk_sum);  // the cell scan is done with it (>= 16 K words)
+  for (int pass = 0; pass < 2; ++pass) {
+    sor_partial_kernel<<<kSorStatBlocks, 1024, 0, st>>>(w, pass, partial);
+    D2PC_CHECK_LAUNCH();
+    sor_finish_kernel<<<1, 32, 0, st>>>(w, pass, partial, std_ratio, d_stats);
+    D2PC_CHECK_LAUNCH();
+  }
   sor_keep_count_kernel<<<row_blocks, kSorThreads, 0, st>>>(w);
   D2PC_CHECK_LAUNCH();
   sor_tile_scan_kernel<<<1, kSorScanThreads, 0, st>>>(w, d_out_count);
