@@ -7,68 +7,98 @@
 //   mean    = sum(avg[avg > 0]) / N ;  std = sqrt(sum((avg - mean)^2 [avg > 0]) / (N - 1))
 //   keep i  iff 0 < avg[i] < mean + std_ratio * std          (rows keep their order)
 //
-// Exact k-NN on the device with a uniform grid over the cloud's bounding box:
-//   begin    cell size h such that the grid has at most kSorCells cells (one thread)
-//   count    cell of every point, per-cell counts (atomics)
-//   scan     exclusive prefix over the cells (block scan, scan of block sums, add)
-//   scatter  points copied into cell order (float32 x, y, z)
-//   query    one thread per point: own cell, then shells of growing Chebyshev radius R; the sorted
-//            list of the k smallest d2 lives in local memory; the search stops as soon as the k-th
-//            distance is no larger than the distance to the unvisited region (R*h + distance to the
-//            own cell's nearest face), which makes the result exact, not approximate
-//   stats    deterministic two-pass reduction by one CTA -> threshold
+// Exact k-NN on the device with a HASHED uniform grid (only occupied cells exist):
+//   begin    kSorTrials candidate cell sizes around (volume / n)^(1/3)
+//   trial    for every candidate: insert the cell keys into the hash table, count the occupied cells;
+//   choose   the finest cell size that still holds >= kSorTargetOcc points per occupied cell on average
+//            (a surface fills far fewer cells than its bounding box has, a volume fills them all; the
+//            occupancy, not the box, decides)
+//   build    insert again with the chosen size: slot of every point, per-slot counts
+//   scan     exclusive prefix over the table slots (block scan, scan of block sums, add)
+//   scatter  points copied into slot order (float32 x, y, z) with their source rows
+//   query    one thread per point IN SLOT ORDER (the lanes of a warp share candidate lists): own cell, then
+//            shells of growing Chebyshev radius R, each neighbour cell found by one hash probe; a float32
+//            estimate rejects most candidates before the exact float64 distance; the sorted list of the
+//            k smallest d2 lives in local memory; the search stops as soon as the k-th distance is no
+//            larger than the distance to everything unvisited, which makes the result exact
+//   stats    deterministic two-pass reduction -> threshold
 //   compact  per-tile kept counts, scan, ordered copy of kept rows + their source indices
 #include "d2pc_device.cuh"
 
 namespace d2pc {
 
-constexpr uint32_t kSorCells = 1u << 24;  // grid cells (dense arrays): 16 M
 constexpr int kSorMaxK = 64;
 constexpr int kSorThreads = 256;
 constexpr int kSorScanThreads = 1024;
+constexpr int kSorTrials = 8;
+constexpr double kSorTrialStep = 1.5;     // ratio between consecutive candidate cell sizes
+constexpr double kSorTargetOcc = 5.0;     // points per occupied cell aimed at
+constexpr int kSorCoordBits = 20;         // cell coordinates per axis
+constexpr unsigned long long kSorEmpty = 0xFFFFFFFFFFFFFFFFull;
 
 struct __align__(256) SorHeader {
-  double mn[3];
+  double mn[3], ext[3];
   double h, slack;
-  int32_t dim[3];
-  uint32_t ncells, n;
+  double trial_h[kSorTrials];
+  uint32_t trial_occ[kSorTrials];
+  int32_t dim[3];       // cells per axis for the chosen size (coordinates are clamped to it)
+  uint32_t n, chosen;
   double cloud_mean, std_dev, thr;
-  double sum1, sum2;
 };
 
 struct SorWs {
   SorHeader *hdr;
-  uint32_t *cell_off;   // [kSorCells + 1]
-  uint32_t *cell_cnt;   // [kSorCells]  counts, then scatter cursors
-  uint32_t *blk_sum;    // [kSorCells / 1024 + 1]
-  uint32_t *pt_cell;    // [N]
-  float *sorted;        // [N][3]  points in cell order
-  uint32_t *sorted_idx; // [N]     source row of every sorted point
-  double *avg;          // [N]
-  uint32_t *tile_cnt;   // [N / 256 + 1]
+  unsigned long long *keys;  // [cap]     cell key per table slot (kSorEmpty = free)
+  uint32_t *cell_off;        // [cap + 1] first sorted point of every slot
+  uint32_t *cell_cnt;        // [cap]     counts, then scatter cursors
+  uint32_t *blk_sum;         // [cap / 1024 + 1] (>= 256 doubles: reused by the statistics)
+  uint32_t *pt_cell;         // [N]       slot of every point
+  float *sorted;             // [N][3]    points in slot order
+  uint32_t *sorted_idx;      // [N]       source row of every sorted point
+  double *avg;               // [N]
+  uint32_t *tile_cnt;        // [N / 256 + 1]
+  uint32_t cap;              // table slots: power of two >= 2 N
 };
 
+inline uint32_t sor_capacity(uint32_t n_rows) {
+  uint32_t c = 1u << 16;
+  while (c < 2u * n_rows && c < 0x80000000u) c <<= 1;
+  return c;
+}
 inline size_t sor_ws_bytes(uint32_t n_rows) {
+  const size_t cap = sor_capacity(n_rows);
   size_t b = sizeof(SorHeader);
-  b += align_up((size_t)(kSorCells + 1) * 4, 256) + align_up((size_t)kSorCells * 4, 256);
-  b += align_up((size_t)(kSorCells / kSorScanThreads + 1) * 4, 256);
+  b += align_up(cap * 8, 256) + align_up((cap + 1) * 4, 256) + align_up(cap * 4, 256);
+  b += align_up((cap / kSorScanThreads + 1) * 4 + 2048, 256);   // + room for 256 float64 partial sums
   b += 2 * align_up((size_t)n_rows * 4, 256) + align_up((size_t)n_rows * 12, 256) + align_up((size_t)n_rows * 8, 256);
   b += align_up((size_t)(n_rows / kSorThreads + 1) * 4, 256);
   return b;
 }
 inline SorWs sor_ws(void *base, uint32_t n_rows) {
   SorWs w;
+  const size_t cap = sor_capacity(n_rows);
   char *p = (char *)base;
-  w.hdr = (SorHeader *)p;      p += sizeof(SorHeader);
-  w.cell_off = (uint32_t *)p;  p += align_up((size_t)(kSorCells + 1) * 4, 256);
-  w.cell_cnt = (uint32_t *)p;  p += align_up((size_t)kSorCells * 4, 256);
-  w.blk_sum = (uint32_t *)p;   p += align_up((size_t)(kSorCells / kSorScanThreads + 1) * 4, 256);
-  w.pt_cell = (uint32_t *)p;   p += align_up((size_t)n_rows * 4, 256);
-  w.sorted = (float *)p;       p += align_up((size_t)n_rows * 12, 256);
-  w.sorted_idx = (uint32_t *)p; p += align_up((size_t)n_rows * 4, 256);
-  w.avg = (double *)p;         p += align_up((size_t)n_rows * 8, 256);
+  w.hdr = (SorHeader *)p;               p += sizeof(SorHeader);
+  w.keys = (unsigned long long *)p;     p += align_up(cap * 8, 256);
+  w.cell_off = (uint32_t *)p;           p += align_up((cap + 1) * 4, 256);
+  w.cell_cnt = (uint32_t *)p;           p += align_up(cap * 4, 256);
+  w.blk_sum = (uint32_t *)p;            p += align_up((cap / kSorScanThreads + 1) * 4 + 2048, 256);
+  w.pt_cell = (uint32_t *)p;            p += align_up((size_t)n_rows * 4, 256);
+  w.sorted = (float *)p;                p += align_up((size_t)n_rows * 12, 256);
+  w.sorted_idx = (uint32_t *)p;         p += align_up((size_t)n_rows * 4, 256);
+  w.avg = (double *)p;                  p += align_up((size_t)n_rows * 8, 256);
   w.tile_cnt = (uint32_t *)p;
+  w.cap = (uint32_t)cap;
   return w;
+}
+
+__device__ __forceinline__ uint32_t sor_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+__device__ __forceinline__ unsigned long long sor_key(int32_t c0, int32_t c1, int32_t c2) {
+  return ((unsigned long long)(uint32_t)c0 << (2 * kSorCoordBits)) | ((unsigned long long)(uint32_t)c1 << kSorCoordBits) |
+         (unsigned long long)(uint32_t)c2;
 }
 
 __global__ void sor_begin_kernel(SorWs w, const uint32_t *count, const float *bounds) {
@@ -76,54 +106,122 @@ __global__ void sor_begin_kernel(SorWs w, const uint32_t *count, const float *bo
   SorHeader *h = w.hdr;
   const uint32_t n = *count;
   h->n = n;
-  double ext[3], mx = 0.0;
+  double mx = 0.0, vol = 1.0;
+  int nd = 0;
   for (int a = 0; a < 3; ++a) {
     const double lo = (double)bounds[a], hi = (double)bounds[3 + a];
     h->mn[a] = (n > 0 && lo == lo) ? lo : 0.0;
-    ext[a] = (n > 0 && hi == hi && lo == lo && hi > lo) ? hi - lo : 0.0;
-    if (ext[a] > mx) mx = ext[a];
+    h->ext[a] = (n > 0 && hi == hi && lo == lo && hi > lo) ? hi - lo : 0.0;
+    if (h->ext[a] > mx) mx = h->ext[a];
+    if (h->ext[a] > 0.0) { vol *= h->ext[a]; ++nd; }
   }
-  // about eight cells per point (most stay empty for surface-like clouds), never more than kSorCells
-  double cap = 8.0 * (double)n;
-  cap = cap < 64.0 ? 64.0 : (cap > (double)kSorCells ? (double)kSorCells : cap);
-  double cs = mx > 0.0 ? mx / 1048576.0 : 1.0;
-  int32_t d[3];
-  while (true) {
-    double prod = 1.0;
-    for (int a = 0; a < 3; ++a) {
-      const double q = floor(ext[a] / cs) + 1.0;
-      d[a] = q < 2.0e9 ? (int32_t)q : 2000000000;
-      prod *= (double)d[a];
-    }
-    if (prod <= cap) break;
-    cs *= 1.125;
+  // middle candidate: the size at which the non-degenerate box has about n cells; never finer than the
+  // coordinate range allows
+  double base = (n > 0 && nd > 0) ? pow(vol / (double)n, 1.0 / (double)nd) : 1.0;
+  const double floor_h = mx > 0.0 ? mx / (double)((1 << kSorCoordBits) - 2) : 1.0;
+  for (int t = 0; t < kSorTrials; ++t) {
+    double ht = base * pow(kSorTrialStep, (double)(3 - t));  // t = 0 coarsest ... kSorTrials - 1 finest
+    h->trial_h[t] = ht > floor_h ? ht : floor_h;
+    h->trial_occ[t] = 0;
   }
-  h->h = cs;
   h->slack = 1e-9 * mx + 1e-300;
-  h->dim[0] = d[0]; h->dim[1] = d[1]; h->dim[2] = d[2];
-  h->ncells = (uint32_t)d[0] * (uint32_t)d[1] * (uint32_t)d[2];
 }
 
-__device__ __forceinline__ void sor_cell_coords(const SorHeader *h, double x, double y, double z, int32_t c[3]) {
+__device__ __forceinline__ void sor_cell_coords(const SorHeader *h, double cs, double x, double y, double z, int32_t c[3]) {
   const double p[3] = {x, y, z};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const double q = floor((p[a] - h->mn[a]) / h->h);
-    int32_t i = q > 0.0 ? (q < 2.0e9 ? (int32_t)q : 2000000000) : 0;  // NaN -> 0
-    c[a] = min(i, h->dim[a] - 1);
+    double q = floor((p[a] - h->mn[a]) / cs);
+    const double top = floor(h->ext[a] / cs);  // last cell of the axis: the maximum itself must not open a new one
+    q = q < top ? q : top;
+    c[a] = q > 0.0 ? (q < 1048574.0 ? (int32_t)q : 1048574) : 0;  // NaN -> 0
+  }
+}
+
+// insert a key; returns the slot, *fresh = this call created the entry
+__device__ __forceinline__ uint32_t sor_insert(const SorWs &w, unsigned long long key, bool *fresh) {
+  const uint32_t mask = w.cap - 1u;
+  uint32_t slot = sor_hash(key) & mask;
+  *fresh = false;
+  while (true) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&w.keys[slot]);
+    if (k == kSorEmpty) {
+      k = atomicCAS(&w.keys[slot], kSorEmpty, key);
+      if (k == kSorEmpty) { *fresh = true; return slot; }
+    }
+    if (k == key) return slot;
+    slot = (slot + 1u) & mask;
+  }
+}
+__device__ __forceinline__ bool sor_find(const SorWs &w, unsigned long long key, uint32_t *slot_out) {
+  const uint32_t mask = w.cap - 1u;
+  uint32_t slot = sor_hash(key) & mask;
+  while (true) {
+    const unsigned long long k = w.keys[slot];
+    if (k == key) { *slot_out = slot; return true; }
+    if (k == kSorEmpty) return false;
+    slot = (slot + 1u) & mask;
+  }
+}
+
+__global__ void sor_clear_kernel(SorWs w) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < w.cap; i += (size_t)gridDim.x * blockDim.x) {
+    w.keys[i] = kSorEmpty;
+    w.cell_cnt[i] = 0u;
+  }
+}
+
+// occupied cells for candidate size `trial`
+__global__ void __launch_bounds__(kSorThreads) sor_trial_kernel(SorWs w, const float *xyz, int trial) {
+  __shared__ uint32_t s_new;
+  if (threadIdx.x == 0) s_new = 0;
+  __syncthreads();
+  SorHeader *h = w.hdr;
+  const uint32_t n = h->n;
+  const double cs = h->trial_h[trial];
+  uint32_t mine = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int32_t c[3];
+    sor_cell_coords(h, cs, (double)__ldg(xyz + 3 * (size_t)i), (double)__ldg(xyz + 3 * (size_t)i + 1),
+                    (double)__ldg(xyz + 3 * (size_t)i + 2), c);
+    bool fresh;
+    sor_insert(w, sor_key(c[0], c[1], c[2]), &fresh);
+    mine += fresh ? 1u : 0u;
+  }
+  mine = warp_sum(mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_new, mine);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) atomicAdd(&h->trial_occ[trial], s_new);
+}
+
+__global__ void sor_choose_kernel(SorWs w) {
+  if (threadIdx.x != 0) return;
+  SorHeader *h = w.hdr;
+  int best = 0;
+  for (int t = 0; t < kSorTrials; ++t) {
+    const double occ = h->trial_occ[t] ? (double)h->n / (double)h->trial_occ[t] : 0.0;
+    if (occ >= kSorTargetOcc) best = t;  // finest size that still fills its cells
+  }
+  h->chosen = (uint32_t)best;
+  h->h = h->trial_h[best];
+  for (int a = 0; a < 3; ++a) {
+    const double q = floor(h->ext[a] / h->h) + 1.0;
+    h->dim[a] = q < 1048575.0 ? (int32_t)q : 1048575;
   }
 }
 
 __global__ void __launch_bounds__(kSorThreads) sor_count_kernel(SorWs w, const float *xyz) {
   const SorHeader *h = w.hdr;
   const uint32_t n = h->n;
+  const double cs = h->h;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int32_t c[3];
-    sor_cell_coords(h, (double)__ldg(xyz + 3 * (size_t)i), (double)__ldg(xyz + 3 * (size_t)i + 1),
+    sor_cell_coords(h, cs, (double)__ldg(xyz + 3 * (size_t)i), (double)__ldg(xyz + 3 * (size_t)i + 1),
                     (double)__ldg(xyz + 3 * (size_t)i + 2), c);
-    const uint32_t cell = ((uint32_t)c[0] * (uint32_t)h->dim[1] + (uint32_t)c[1]) * (uint32_t)h->dim[2] + (uint32_t)c[2];
-    w.pt_cell[i] = cell;
-    atomicAdd(&w.cell_cnt[cell], 1u);
+    bool fresh;
+    const uint32_t slot = sor_insert(w, sor_key(c[0], c[1], c[2]), &fresh);
+    w.pt_cell[i] = slot;
+    atomicAdd(&w.cell_cnt[slot], 1u);
   }
 }
 
@@ -149,7 +247,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp
 // the counts are zeroed so that the array can serve as the scatter cursors
 __global__ void __launch_bounds__(kSorScanThreads) sor_scan1_kernel(SorWs w) {
   __shared__ uint32_t s_warp[32];
-  const uint32_t nc = w.hdr->ncells;
+  const uint32_t nc = w.cap;
   const uint32_t i = blockIdx.x * (uint32_t)kSorScanThreads + threadIdx.x;
   if (blockIdx.x * (uint32_t)kSorScanThreads >= nc) return;
   const uint32_t v = i < nc ? w.cell_cnt[i] : 0u;
@@ -162,7 +260,7 @@ __global__ void __launch_bounds__(kSorScanThreads) sor_scan1_kernel(SorWs w) {
 __global__ void __launch_bounds__(kSorScanThreads) sor_scan2_kernel(SorWs w) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
-  const uint32_t nb = (w.hdr->ncells + kSorScanThreads - 1) / kSorScanThreads;
+  const uint32_t nb = (w.cap + kSorScanThreads - 1) / kSorScanThreads;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   for (uint32_t base = 0; base < nb; base += kSorScanThreads) {
@@ -178,7 +276,7 @@ __global__ void __launch_bounds__(kSorScanThreads) sor_scan2_kernel(SorWs w) {
 }
 // phase 3: add the block offsets; the entry past the last cell holds n
 __global__ void __launch_bounds__(kSorScanThreads) sor_scan3_kernel(SorWs w) {
-  const uint32_t nc = w.hdr->ncells;
+  const uint32_t nc = w.cap;
   const uint32_t i = blockIdx.x * (uint32_t)kSorScanThreads + threadIdx.x;
   if (i < nc) w.cell_off[i] += w.blk_sum[blockIdx.x];
   if (i == nc) w.cell_off[nc] = w.hdr->n;
@@ -236,6 +334,13 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
   }
 }
 
+// a neighbour cell by key: one hash probe; most cells of a shell do not exist
+__device__ __forceinline__ void sor_visit_key(const SorWs &w, unsigned long long key, const double q[3], const float qf[3],
+                                              double *best, int k, float &thrf) {
+  uint32_t slot;
+  if (sor_find(w, key, &slot)) sor_visit_cell(w, slot, q, qf, best, k, thrf);
+}
+
 // Queries run in CELL order (thread j owns the j-th sorted point): the lanes of a warp then share their
 // query cell, walk the same candidate lists with the same trip counts and read the same addresses.
 __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int nb_neighbors) {
@@ -252,8 +357,10 @@ __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int 
   float thrf = __int_as_float(0x7F800000);
   const int32_t nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
   const uint32_t cell = w.pt_cell[i];
-  const int32_t c2 = (int32_t)(cell % (uint32_t)nz), c1 = (int32_t)((cell / (uint32_t)nz) % (uint32_t)ny),
-                c0 = (int32_t)(cell / ((uint32_t)nz * (uint32_t)ny));
+  const unsigned long long ckey = w.keys[cell];
+  const int32_t cm = (1 << kSorCoordBits) - 1;
+  const int32_t c0 = (int32_t)(ckey >> (2 * kSorCoordBits)) & cm, c1 = (int32_t)(ckey >> kSorCoordBits) & cm,
+                c2 = (int32_t)ckey & cm;
   const int32_t c[3] = {c0, c1, c2};
   // distances from the query to the faces of its own cell (0 if rounding put it outside)
   double dlo[3], dhi[3];
@@ -288,26 +395,20 @@ __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int 
     for (int side = 0; side < 2; ++side) {
       const int32_t a0 = side ? c0 + R : c0 - R;
       if (a0 < 0 || a0 >= nx) continue;
-      for (int32_t a1 = y0; a1 <= y1; ++a1) {
-        const uint32_t row = ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz;
-        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q, qf, best, k, thrf);
-      }
+      for (int32_t a1 = y0; a1 <= y1; ++a1)
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf);
     }
     for (int side = 0; side < 2; ++side) {
       const int32_t a1 = side ? c1 + R : c1 - R;
       if (a1 < 0 || a1 >= ny) continue;
-      for (int32_t a0 = xi0; a0 <= xi1; ++a0) {
-        const uint32_t row = ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz;
-        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_cell(w, row + (uint32_t)a2, q, qf, best, k, thrf);
-      }
+      for (int32_t a0 = xi0; a0 <= xi1; ++a0)
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf);
     }
     for (int side = 0; side < 2; ++side) {
       const int32_t a2 = side ? c2 + R : c2 - R;
       if (a2 < 0 || a2 >= nz) continue;
       for (int32_t a0 = xi0; a0 <= xi1; ++a0)
-        for (int32_t a1 = yi0; a1 <= yi1; ++a1)
-          sor_visit_cell(w, ((uint32_t)a0 * (uint32_t)ny + (uint32_t)a1) * (uint32_t)nz + (uint32_t)a2, q, qf, best, k,
-                         thrf);
+        for (int32_t a1 = yi0; a1 <= yi1; ++a1) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf);
     }
   }
   double s = 0.0;
@@ -427,12 +528,20 @@ extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const ui
   if (scratch_bytes < sor_ws_bytes(capacity_rows)) return D2PC_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
   SorWs w = sor_ws(d_scratch, capacity_rows);
-  cudaError_t e = cudaMemsetAsync(w.cell_cnt, 0, (size_t)kSorCells * 4, st);
-  if (e != cudaSuccess) return record_cuda_error(e);
   const uint32_t row_blocks = (capacity_rows + kSorThreads - 1) / kSorThreads;
   const uint32_t stride_blocks = min(row_blocks, 148u * 16u);
-  const uint32_t cell_blocks = kSorCells / kSorScanThreads + 1;
+  const uint32_t cell_blocks = w.cap / kSorScanThreads + 1;
   sor_begin_kernel<<<1, 32, 0, st>>>(w, d_count, d_bounds);
+  D2PC_CHECK_LAUNCH();
+  for (int t = 0; t < kSorTrials; ++t) {  // occupied cells for every candidate cell size
+    sor_clear_kernel<<<148 * 8, 256, 0, st>>>(w);
+    D2PC_CHECK_LAUNCH();
+    sor_trial_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz, t);
+    D2PC_CHECK_LAUNCH();
+  }
+  sor_choose_kernel<<<1, 32, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_clear_kernel<<<148 * 8, 256, 0, st>>>(w);
   D2PC_CHECK_LAUNCH();
   sor_count_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz);
   D2PC_CHECK_LAUNCH();
@@ -446,7 +555,7 @@ extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const ui
   D2PC_CHECK_LAUNCH();
   sor_query_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, nb_neighbors);
   D2PC_CHECK_LAUNCH();
-  double *partial = reinterpret_cast<double *>(w.blk_sum);  // the cell scan is done with it (>= 16 K words)
+  double *partial = reinterpret_cast<double *>(w.blk_sum);  // the cell scan is done with it
   for (int pass = 0; pass < 2; ++pass) {
     sor_partial_kernel<<<kSorStatBlocks, 1024, 0, st>>>(w, pass, partial);
     D2PC_CHECK_LAUNCH();
