@@ -436,6 +436,9 @@ def run_extras(m, device):
     # row f3: writer byte layouts on one 1080p cloud (kernels only)
     from profiles.writers_bench import bench as writers_bench
     out["writers_1080p"] = writers_bench()
+    # row f1: statistical outlier removal on the stage's own clouds
+    from profiles.sor_bench import bench as sor_bench
+    out["sor_k20"] = sor_bench()
     # the drop-in call itself: NumPy in, NumPy out, one image (what backend/app.py:468 does per request)
     import numpy as np
     rng = np.random.default_rng(1)
