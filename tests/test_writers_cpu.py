@@ -101,3 +101,26 @@ def test_preview_stride(hm):
         s = hm.hm_preview_stride(n, 20000)
         assert len(pp) == (0 if n == 0 else (n - 1) // s + 1)
         assert len(pp) <= 40000
+
+
+def test_sor_oracle_against_brute_force():
+    """Row f1: the oracle's k-NN (scipy cKDTree) against an O(n^2) NumPy evaluation of the same definition
+    (squared distances accumulated axis by axis in float64, self included, ascending sum)."""
+    rng = np.random.default_rng(80)
+    p = rng.standard_normal((400, 3)).astype(np.float32)
+    p[:7] += 9.0                      # outliers
+    p[50:60] = p[40:50]               # exact duplicates
+    keep, avg, (mean, std, thr) = O.statistical_outlier_removal(p, 20, 2.0)
+    q = p.astype(np.float64)
+    d2 = (q[:, None, 0] - q[None, :, 0]) ** 2
+    d2 = d2 + (q[:, None, 1] - q[None, :, 1]) ** 2
+    d2 = d2 + (q[:, None, 2] - q[None, :, 2]) ** 2
+    near = np.sqrt(np.sort(d2, axis=1)[:, :20])
+    want = np.cumsum(near, axis=1)[:, -1] / 20
+    assert np.array_equal(avg, want)
+    pos = want > 0
+    m = np.cumsum(np.where(pos, want, 0.0))[-1] / len(p)
+    s = np.sqrt(np.cumsum(np.where(pos, (want - m) ** 2, 0.0))[-1] / (len(p) - 1))
+    assert (mean, std) == (m, s)
+    assert np.array_equal(keep, np.nonzero(pos & (want < m + 2.0 * s))[0])
+    assert not set(range(7)) & set(keep.tolist())     # the far points are removed
