@@ -116,3 +116,60 @@ def test_config3_batch_of_1080p_frames(m):
         assert_bits_equal(xyz[b], po, f"frame {b}")
     res2 = eng.process(cfg, d, im)
     assert torch.equal(res2.xyz, res.xyz) and torch.equal(res2.rgb, res.rgb)
+
+
+def test_kernels_stay_inside_their_output_slots(m):
+    """Canary rows before and after every output buffer must survive (the pool has no compute-sanitizer):
+    unmasked / masked / strided / bounds emit on awkward sizes, then voxels and the writer records."""
+    import ctypes as C
+
+    import torch
+    PAD = 64  # floats on each side (256 B keeps the 16-byte alignment the ABI asks for)
+    rng = np.random.default_rng(90)
+    for (H, W, h, w, dens, zr) in [(97, 164, 97, 164, "high", None), (97, 164, 40, 70, "high", (1.0, 9.0)),
+                                   (64, 1040, 64, 1040, "medium", None), (50, 47, 50, 47, "low", (0.5, 9.5)),
+                                   (33, 4, 33, 4, "high", (2.0, 3.0))]:
+        B = 3
+        eng = m.FrameEngine(H, W, h, w, batch=B)
+        cfg = eng.make_config(density=dens, z_range=zr, want_bounds=True)
+        n = eng.points_per_frame(cfg)
+        d = torch.from_numpy((rng.random((B, h, w)) * 20).astype(np.float32)).cuda()
+        im = torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).cuda()
+        bufs = []
+        for _ in range(2):
+            flat = torch.full((B * n * 3 + 2 * PAD,), -777.0, dtype=torch.float32, device="cuda")
+            bufs.append(flat)
+        xyz = bufs[0][PAD:PAD + B * n * 3].view(B, n, 3)
+        rgb = bufs[1][PAD:PAD + B * n * 3].view(B, n, 3)
+        res = eng.process(cfg, d, im, xyz=xyz, rgb=rgb)
+        torch.cuda.synchronize()
+        for flat in bufs:
+            assert bool((flat[:PAD] == -777.0).all()) and bool((flat[-PAD:] == -777.0).all()), (H, W, dens, zr)
+        # rows past count[b] of a masked frame are never written
+        for b in range(B):
+            k = int(res.count[b])
+            assert bool((xyz[b, k:] == -777.0).all()) and bool((rgb[b, k:] == -777.0).all())
+            po, co = _oracle(im[b].cpu().numpy(), d[b].cpu().numpy(), density=dens)
+            keep = O.range_mask(po, *zr) if zr else np.ones(len(po), bool)
+            assert_bits_equal(xyz[b, :k].cpu().numpy(), po[keep], "guarded emit")
+    # writer records: exact sizes, canary after the last byte
+    lib = m.load_library()
+    p, c = cases.writer_rows(n=1000)
+    ok = np.isfinite(p).all(axis=1) & (np.abs(p) < 1e6).all(axis=1)
+    xyz = torch.from_numpy(np.ascontiguousarray(p[ok])).cuda()
+    rgb = torch.from_numpy(np.ascontiguousarray(c[ok])).cuda()
+    nrow = xyz.shape[0]
+    cnt = torch.tensor([nrow], dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for rec_bytes, call in ((27, "ply"), (26, "las")):
+        buf = torch.full((nrow * rec_bytes + 256,), 0xAB, dtype=torch.uint8, device="cuda")
+        if call == "ply":
+            assert lib.d2pc_ply_records_enqueue(xyz.data_ptr(), rgb.data_ptr(), cnt.data_ptr(), nrow, buf.data_ptr(), s) == 0
+        else:
+            bounds = torch.cat([xyz.amin(0), xyz.amax(0)]).contiguous()
+            mm = torch.zeros(6, dtype=torch.int32, device="cuda")
+            err = torch.zeros(1, dtype=torch.int32, device="cuda")
+            assert lib.d2pc_las_records_enqueue(xyz.data_ptr(), rgb.data_ptr(), cnt.data_ptr(), nrow, bounds.data_ptr(),
+                                                0.01, buf.data_ptr(), mm.data_ptr(), err.data_ptr(), s) == 0
+        torch.cuda.synchronize()
+        assert bool((buf[nrow * rec_bytes:] == 0xAB).all()), call
