@@ -248,6 +248,14 @@ def run_ours(args):
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # pin this rank to the CPUs next to its GPU before any pinned buffer is allocated (the e2e leg streams
+    # ~65 MB per frame through host memory; a remote NUMA node halves that)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
