@@ -245,6 +245,9 @@ def test_voxel_downsample(m):
             assert np.array_equal(c[order].view(np.uint32), c2[o2].view(np.uint32))
     with pytest.raises(ValueError):
         m.depth_to_point_cloud(img, dep, density="high", voxel_size=1e-9)
+    # a mask that keeps nothing: empty voxel output, no error
+    p, c, idx = m.depth_to_point_cloud(img, dep, density="high", z_range=(20.0, 30.0), voxel_size=0.05, return_voxel_index=True)
+    assert p.shape == (0, 3) and c.shape == (0, 3) and idx.shape == (0, 3)
 
 
 def test_smoothing_larger_frames(m):

@@ -84,3 +84,36 @@ def test_las_and_ply_records(m, tmp_path, monkeypatch):
     assert raw[:4] == b"LASF" and len(raw) == 227 + 26 * len(p) and raw[227:] == want.tobytes()
     with pytest.raises(ValueError):
         m.save_point_cloud(p, c, "obj", "job4")
+
+
+def test_point_cloud_stage_equals_the_separate_drop_ins(m, tmp_path, monkeypatch):
+    """The device-resident pipeline (app.py:468-559 in one pass) returns exactly what the individual
+    drop-ins return when they are chained through host arrays like the reference chains its functions."""
+    rng = np.random.default_rng(62)
+    img = rng.integers(0, 256, (240, 320, 3), dtype=np.uint8)
+    dep = cases.make_depth(259, 343, 21, "scene")
+    monkeypatch.chdir(tmp_path)
+    for fmt in ("ply", "xyz", "las"):
+        out = m.point_cloud_stage(img, dep, density="medium", output_format=fmt, filename="job")
+        p, c = m.depth_to_point_cloud(img, dep, density="medium")
+        p, c = m.refine_point_cloud(p, c)
+        assert out["point_count"] == len(p) and np.array_equal(out["points"], p) and np.array_equal(out["colors"], c)
+        pp, pc = m.preview_lists(p, c)
+        assert out["preview_points"] == pp and out["preview_colors"] == pc
+        assert out["bounds"]["minX"] == float(p[:, 0].min()) and out["bounds"]["maxZ"] == float(p[:, 2].max())
+        path = m.save_point_cloud(p, c, fmt, "ref")
+        got, want = open(out["filepath"], "rb").read(), open(path, "rb").read()
+        if fmt == "las":   # the header carries the creation day; bodies must agree
+            assert got[227:] == want[227:] and got[:4] == b"LASF"
+        else:
+            assert got == want
+        mem = m.point_cloud_stage(img, dep, density="medium", output_format=fmt)   # no filename: bytes in memory
+        assert (mem["file_bytes"][227:] == got[227:]) if fmt == "las" else (mem["file_bytes"] == got)
+    # against the oracle chain as well
+    with __import__("warnings").catch_warnings():
+        __import__("warnings").simplefilter("ignore")
+        po, co = O.depth_to_point_cloud(img, dep, density="medium")
+    keep, _, _ = O.statistical_outlier_removal(po)
+    out = m.point_cloud_stage(img, dep, density="medium", output_format=None)
+    assert np.array_equal(out["points"].view(np.uint32), po[keep].view(np.uint32))
+    assert "file_bytes" not in out
