@@ -373,15 +373,22 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
       stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
                byte_to_float(c2, D2PC_B1));
     }
+    // The tile's rows are contiguous in both outputs (rows * 12 bytes each, a multiple of 16 at 16-byte
+    // aligned addresses): one elected thread hands each staged array to the TMA unit as a bulk
+    // shared -> global copy, the other threads are done.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged rows visible to the async proxy
     __syncthreads();
     const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
     const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
-    const uint32_t nvec = rows * 3u / 4u;  // rows % 4 == 0 here
-    for (uint32_t i = tid; i < nvec; i += kEmitThreads) {
-      stg_stream_f4(ea.xyz + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_xyz + 4 * i));
-      stg_stream_f4(ea.rgb + g0 + 4 * i, *reinterpret_cast<const float4 *>(s_rgb + 4 * i));
+    if (tid == 0) {
+      const uint32_t bytes = rows * 12u;  // rows % 4 == 0 here
+      const uint32_t sx = (uint32_t)__cvta_generic_to_shared(s_xyz), sr = (uint32_t)__cvta_generic_to_shared(s_rgb);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(ea.xyz + g0), "r"(sx), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(ea.rgb + g0), "r"(sr), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging may be released once it has been read
+      if (tile == 0) ea.count[b] = kp.g.N;
     }
-    if (tile == 0 && tid == 0) ea.count[b] = kp.g.N;
   } else {
     // CTA exclusive scan of the per-thread keep counts
     uint32_t incl = my_cnt;
