@@ -52,18 +52,35 @@ __device__ __forceinline__ void reduce_bounds(FrameState *fs, uint32_t mn[3], ui
 
 // Copy n_f floats from shared staging (whose word 0 corresponds to global float index
 // g0 - s_off, i.e. staging is offset so that src and dst share 16 B alignment) to global.
+// The 16-byte aligned middle goes out as one TMA bulk copy issued by thread 0; the (at most three)
+// floats before and after it are stored by single threads.  The caller has executed
+// fence.proxy.async.shared::cta and a __syncthreads() after the last staging write.
 __device__ __forceinline__ void copy_out(const float *s, uint32_t s_off, uint32_t n_f, float *gbase,
                                          size_t g0) {
   float *galigned = gbase + (g0 - s_off);
   const uint32_t span = s_off + n_f;
-  const uint32_t chunks = (span + 3u) >> 2;
-  for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x) {
-    const uint32_t w = c << 2;
-    if (w >= s_off && w + 4u <= span) {
-      stg_stream_f4(galigned + w, *reinterpret_cast<const float4 *>(s + w));
-    } else {
-      for (uint32_t k = 0; k < 4u; ++k)
-        if (w + k >= s_off && w + k < span) stg_stream_f1(galigned + w + k, s[w + k]);
+  const uint32_t w_first = s_off ? 4u : 0u;      // first float of the aligned middle
+  const uint32_t w_last = span & ~3u;            // one past its last float
+  const uint32_t tid = threadIdx.x;
+  if (w_last > w_first) {
+    if (tid == 0) {
+      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s + w_first);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(galigned + w_first), "r"(sa), "r"((w_last - w_first) * 4u) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (tid >= 32 && tid < 36) {        // head: floats [s_off, min(w_first, span))
+      const uint32_t w = s_off + (tid - 32);
+      if (w < w_first && w < span) stg_stream_f1(galigned + w, s[w]);
+    } else if (tid >= 64 && tid < 68) { // tail: floats [w_last, span)
+      const uint32_t w = w_last + (tid - 64);
+      if (w < span) stg_stream_f1(galigned + w, s[w]);
+    }
+  } else {  // fewer than one aligned chunk: a handful of floats
+    if (tid < 8) {
+      const uint32_t w = s_off + tid;
+      if (w < span) stg_stream_f1(galigned + w, s[w]);
     }
   }
 }
@@ -425,6 +442,7 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
       s_rgb[w] = col[3 * k]; s_rgb[w + 1] = col[3 * k + 1]; s_rgb[w + 2] = col[3 * k + 2];
       local++;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0);
     copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0);
@@ -606,6 +624,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
     s_rgb[w] = col[3 * k]; s_rgb[w + 1] = col[3 * k + 1]; s_rgb[w + 2] = col[3 * k + 2];
     local++;
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0);
   copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0);
