@@ -346,6 +346,17 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
       c1 = __byte_perm(q1, q2, 0x5421);   // G1 R1 B2 G2
       c2 = __byte_perm(q2, q3, 0x6542);   // R2 B3 G3 R3
     }
+    if (!MASK) {
+      // colours first: once staged, their registers are free for the float64 chain below
+      float *sr = s_rgb + 12 * tid;
+      // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
+      stage_f4(sr, byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
+               byte_to_float(c1, D2PC_B1));
+      stage_f4(sr + 4, byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3), byte_to_float(c2, D2PC_B0),
+               byte_to_float(c1, D2PC_B3));
+      stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
+               byte_to_float(c2, D2PC_B1));
+    }
     const NormParams np_ = fs->norm;
     const MaskParams mp = load_mask(fs);
     if (np_.simple && fa.pc_simple) {  // uniform per frame
@@ -378,17 +389,10 @@ __global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KPa
   }
   if (!MASK) {
     if (p0 < P) {
-      float *sx = s_xyz + 12 * tid, *sr = s_rgb + 12 * tid;
+      float *sx = s_xyz + 12 * tid;
       stage_f4(sx, o[0], o[1], o[2], o[3]);
       stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
       stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
-      // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
-      stage_f4(sr, byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
-               byte_to_float(c1, D2PC_B1));
-      stage_f4(sr + 4, byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3), byte_to_float(c2, D2PC_B0),
-               byte_to_float(c1, D2PC_B3));
-      stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
-               byte_to_float(c2, D2PC_B1));
     }
     // The tile's rows are contiguous in both outputs (rows * 12 bytes each, a multiple of 16 at 16-byte
     // aligned addresses): one elected thread hands each staged array to the TMA unit as a bulk
