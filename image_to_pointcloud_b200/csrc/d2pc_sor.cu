@@ -35,6 +35,15 @@ constexpr double kSorTrialStep = 1.5;     // ratio between consecutive candidate
 constexpr double kSorTargetOcc = 5.0;     // points per occupied cell aimed at
 constexpr int kSorCoordBits = 20;         // cell coordinates per axis
 constexpr unsigned long long kSorEmpty = 0xFFFFFFFFFFFFFFFFull;
+// Very heavy cells.  Every cloud of this stage contains a structure far smaller than any sensible cell: the
+// pixels clipped at a percentile all get the same tiny z and collapse into a lattice ~1e-7 wide (2% of the
+// points: 42 000 at 1080p, 166 000 at 4K).  They share one cell, and comparing them pairwise is quadratic.
+// Cells above kSorHeavyMin points are therefore sorted by x (one CTA per cell), and a query walks only the
+// window |dx| <= its current k-th distance, outwards from its own x.
+constexpr uint32_t kSorHeavyMin = 4096;
+constexpr uint32_t kSorHeavyMax = 1u << 20;    // one CTA sorts one cell (bitonic, L2 resident)
+constexpr uint32_t kSorMaxHeavy = 256;         // heavy cells handled per call (the rest stay plain lists)
+constexpr uint32_t kSorSortedFlag = 0x80000000u;
 
 struct __align__(256) SorHeader {
   double mn[3], ext[3];
@@ -44,6 +53,7 @@ struct __align__(256) SorHeader {
   int32_t dim[3];       // cells per axis for the chosen size (coordinates are clamped to it)
   uint32_t n, chosen;
   double cloud_mean, std_dev, thr;
+  uint32_t n_heavy, heavy_total;
 };
 
 struct SorWs {
@@ -57,6 +67,10 @@ struct SorWs {
   uint32_t *sorted_idx;      // [N]       source row of every sorted point
   double *avg;               // [N]
   uint32_t *tile_cnt;        // [N / 256 + 1]
+  uint32_t *heavy;           // [2 * kSorMaxHeavy] slot, offset into `pairs`
+  unsigned long long *pairs; // [2 N] (x key << 32 | rank) per heavy cell, padded to a power of two
+  float *tmp_xyz;            // [N][3] scratch for the permutation
+  uint32_t *tmp_idx;         // [N]
   uint32_t cap;              // table slots: power of two >= 2 N
 };
 
@@ -72,6 +86,8 @@ inline size_t sor_ws_bytes(uint32_t n_rows) {
   b += align_up((cap / kSorScanThreads + 1) * 4 + 2048, 256);   // + room for 256 float64 partial sums
   b += 2 * align_up((size_t)n_rows * 4, 256) + align_up((size_t)n_rows * 12, 256) + align_up((size_t)n_rows * 8, 256);
   b += align_up((size_t)(n_rows / kSorThreads + 1) * 4, 256);
+  b += align_up((size_t)2 * kSorMaxHeavy * 4, 256) + align_up((size_t)2 * n_rows * 8 + 8, 256);
+  b += align_up((size_t)n_rows * 12, 256) + align_up((size_t)n_rows * 4, 256);
   return b;
 }
 inline SorWs sor_ws(void *base, uint32_t n_rows) {
@@ -87,7 +103,11 @@ inline SorWs sor_ws(void *base, uint32_t n_rows) {
   w.sorted = (float *)p;                p += align_up((size_t)n_rows * 12, 256);
   w.sorted_idx = (uint32_t *)p;         p += align_up((size_t)n_rows * 4, 256);
   w.avg = (double *)p;                  p += align_up((size_t)n_rows * 8, 256);
-  w.tile_cnt = (uint32_t *)p;
+  w.tile_cnt = (uint32_t *)p;           p += align_up((size_t)(n_rows / kSorThreads + 1) * 4, 256);
+  w.heavy = (uint32_t *)p;              p += align_up((size_t)2 * kSorMaxHeavy * 4, 256);
+  w.pairs = (unsigned long long *)p;    p += align_up((size_t)2 * n_rows * 8 + 8, 256);
+  w.tmp_xyz = (float *)p;               p += align_up((size_t)n_rows * 12, 256);
+  w.tmp_idx = (uint32_t *)p;
   w.cap = (uint32_t)cap;
   return w;
 }
@@ -125,6 +145,8 @@ __global__ void sor_begin_kernel(SorWs w, const uint32_t *count, const float *bo
     h->trial_occ[t] = 0;
   }
   h->slack = 1e-9 * mx + 1e-300;
+  h->n_heavy = 0;
+  h->heavy_total = 0;
 }
 
 __device__ __forceinline__ void sor_cell_coords(const SorHeader *h, double cs, double x, double y, double z, int32_t c[3]) {
@@ -293,6 +315,77 @@ __global__ void __launch_bounds__(kSorThreads) sor_scatter_kernel(SorWs w, const
   }
 }
 
+// ---- very heavy cells: list, offsets, per-cell sort by x ---------------------------------------------
+__global__ void __launch_bounds__(256) sor_heavy_list_kernel(SorWs w) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < w.cap; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = w.cell_off[i + 1] - w.cell_off[i];
+    w.cell_cnt[i] = 0u;   // free after the scatter: from here on it only carries the "sorted" flag
+    if (c > kSorHeavyMin && c <= kSorHeavyMax) {
+      const uint32_t k = atomicAdd(&w.hdr->n_heavy, 1u);
+      if (k < kSorMaxHeavy) w.heavy[2 * k] = (uint32_t)i;
+    }
+  }
+}
+__device__ __forceinline__ uint32_t sor_pow2(uint32_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+__global__ void sor_heavy_offsets_kernel(SorWs w) {
+  if (threadIdx.x != 0) return;
+  SorHeader *h = w.hdr;
+  if (h->n_heavy > kSorMaxHeavy) h->n_heavy = kSorMaxHeavy;
+  uint32_t off = 0;
+  for (uint32_t k = 0; k < h->n_heavy; ++k) {
+    const uint32_t slot = w.heavy[2 * k];
+    w.heavy[2 * k + 1] = off;
+    off += sor_pow2(w.cell_off[slot + 1] - w.cell_off[slot]);  // sum <= 2 n
+  }
+  h->heavy_total = off;
+}
+// one CTA per heavy cell: bitonic sort of (x key, rank) pairs in global memory (L2 resident), then the
+// cell's segment of `sorted` / `sorted_idx` is permuted into x order and the cell is flagged as sorted
+__global__ void __launch_bounds__(1024) sor_heavy_sort_kernel(SorWs w) {
+  const uint32_t b = blockIdx.x;
+  if (b >= w.hdr->n_heavy) return;
+  const uint32_t slot = w.heavy[2 * b];
+  const uint32_t s = w.cell_off[slot], cnt = w.cell_off[slot + 1] - s;
+  const uint32_t m = sor_pow2(cnt);
+  unsigned long long *P = w.pairs + w.heavy[2 * b + 1];
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  for (uint32_t r = tid; r < m; r += nt) {
+    P[r] = r < cnt ? (((unsigned long long)float_to_key(w.sorted[3 * (size_t)(s + r)]) << 32) | r) : ~0ull;
+    if (r < cnt) {
+      w.tmp_xyz[3 * (size_t)(s + r)] = w.sorted[3 * (size_t)(s + r)];
+      w.tmp_xyz[3 * (size_t)(s + r) + 1] = w.sorted[3 * (size_t)(s + r) + 1];
+      w.tmp_xyz[3 * (size_t)(s + r) + 2] = w.sorted[3 * (size_t)(s + r) + 2];
+      w.tmp_idx[s + r] = w.sorted_idx[s + r];
+    }
+  }
+  __syncthreads();
+  const uint32_t half = m >> 1;
+  for (uint32_t kk = 2; kk <= m; kk <<= 1) {
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = tid; t < half; t += nt) {
+        const uint32_t a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t c = a | j;
+        const unsigned long long x = P[a], y = P[c];
+        const bool up = (a & kk) == 0;
+        if ((x > y) == up) { P[a] = y; P[c] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t r = tid; r < cnt; r += nt) {
+    const uint32_t src = s + (uint32_t)(P[r] & 0xFFFFFFFFull);
+    w.sorted[3 * (size_t)(s + r)] = w.tmp_xyz[3 * (size_t)src];
+    w.sorted[3 * (size_t)(s + r) + 1] = w.tmp_xyz[3 * (size_t)src + 1];
+    w.sorted[3 * (size_t)(s + r) + 2] = w.tmp_xyz[3 * (size_t)src + 2];
+    w.sorted_idx[s + r] = w.tmp_idx[src];
+  }
+  if (tid == 0) w.cell_cnt[slot] = kSorSortedFlag;
+}
+
 // float32 upper bound of the current k-th squared distance (inf while fewer than k points were seen)
 __device__ __forceinline__ float sor_filter(double kth) {
   return __double2float_ru(kth) * 1.000001f;
@@ -304,7 +397,55 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
                                                double *best, int k, float &thrf) {
   const uint32_t s = w.cell_off[cell], e = w.cell_off[cell + 1];
   constexpr int U = 4;  // candidates in flight per iteration (independent loads and float32 estimates)
-  for (uint32_t j0 = s; j0 < e; j0 += U) {
+  if (w.cell_cnt[cell] & kSorSortedFlag) {
+    // Very heavy cell, points sorted by x: walk outwards from the query's x, U candidates per side and step,
+    // while dx^2 can still beat the k-th distance (float32 estimate, same conservative margin as below).
+    uint32_t lo = s, hi = e;
+    while (lo < hi) {  // first point with x >= q.x
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (w.sorted[3 * (size_t)mid] < qf[0]) lo = mid + 1; else hi = mid;
+    }
+    uint32_t r = lo;   // next candidate to the right
+    uint32_t l = lo;   // next candidate to the left is l - 1
+    bool go_r = r < e, go_l = l > s;
+    while ((go_r || go_l) && best[k - 1] > 0.0) {  // k coincident points: nothing can be closer
+      float p[2 * U][3];
+      bool ok[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // independent loads first
+        ok[u] = go_r && r + (uint32_t)u < e;
+        ok[U + u] = go_l && l >= s + 1u + (uint32_t)u;
+        const uint32_t jr = ok[u] ? r + (uint32_t)u : s, jl = ok[U + u] ? l - 1u - (uint32_t)u : s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { p[u][a] = w.sorted[3 * (size_t)jr + a]; p[U + u][a] = w.sorted[3 * (size_t)jl + a]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 2 * U; ++u) {  // in order of growing |dx| on each side
+        const bool right = u < U;
+        if (!ok[u] || (right ? !go_r : !go_l)) continue;
+        const float fx = qf[0] - p[u][0];
+        if (fx * fx > thrf) { if (right) go_r = false; else go_l = false; continue; }
+        const float fy = qf[1] - p[u][1], fz = qf[2] - p[u][2];
+        const float d2f = fx * fx + fy * fy + fz * fz;
+        if (d2f <= thrf) {
+          const double dx = q[0] - (double)p[u][0], dy = q[1] - (double)p[u][1], dz = q[2] - (double)p[u][2];
+          double d2 = dx * dx;
+          d2 += dy * dy;
+          d2 += dz * dz;
+          if (d2 < best[k - 1]) {
+            int t = k - 1;
+            while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
+            best[t] = d2;
+            thrf = sor_filter(best[k - 1]);
+          }
+        }
+      }
+      if (go_r) { r += U; go_r = r < e; }
+      if (go_l) { l = l >= s + (uint32_t)U ? l - (uint32_t)U : s; go_l = l > s; }
+    }
+    return;
+  }
+  for (uint32_t j0 = s; j0 < e && best[k - 1] > 0.0; j0 += U) {  // (k coincident points end the search)
     float p[U][3], d2f[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -384,7 +525,7 @@ __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int 
       if (c[a] + R <= dim[a] - 1) reach = fmin(reach, (double)(R - 1) * h->h + dhi[a]);
     }
     reach -= h->slack;
-    if (reach > 0.0 && best[k - 1] <= reach * reach) break;
+    if ((reach > 0.0 && best[k - 1] <= reach * reach) || best[k - 1] == 0.0) break;
     // shell of Chebyshev radius R, clipped to the grid, as six slabs (no cell is visited twice):
     //   x faces: a0 = c0 -+ R, full (a1, a2) range;  y faces: a1 = c1 -+ R, a0 interior;  z faces: a0, a1 interior
     const int32_t x0 = max(c0 - R, 0), x1 = min(c0 + R, nx - 1);
@@ -552,6 +693,12 @@ extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const ui
   sor_scan3_kernel<<<cell_blocks, kSorScanThreads, 0, st>>>(w);
   D2PC_CHECK_LAUNCH();
   sor_scatter_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz);
+  D2PC_CHECK_LAUNCH();
+  sor_heavy_list_kernel<<<148 * 8, 256, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_heavy_offsets_kernel<<<1, 32, 0, st>>>(w);
+  D2PC_CHECK_LAUNCH();
+  sor_heavy_sort_kernel<<<kSorMaxHeavy, 1024, 0, st>>>(w);
   D2PC_CHECK_LAUNCH();
   sor_query_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, nb_neighbors);
   D2PC_CHECK_LAUNCH();
