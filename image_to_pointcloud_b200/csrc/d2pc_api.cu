@@ -22,9 +22,6 @@ int validate_config(const D2pcConfig *c) {
   if ((unsigned long long)c->img_h * (unsigned long long)c->img_w >= (1ull << 31)) return D2PC_ERR_INVALID_ARGUMENT;
   if ((unsigned long long)c->dep_h * (unsigned long long)c->dep_w >= (1ull << 31)) return D2PC_ERR_INVALID_ARGUMENT;
   const bool resized = !(c->dep_h == c->img_h && c->dep_w == c->img_w);
-  // cv2.resize leaves the IPP path for 1-pixel-wide/high sources (SURVEY 8a-1 model does not
-  // cover OpenCV's generic fallback): refuse instead of returning slightly different numbers.
-  if (resized && (c->dep_h < 2 || c->dep_w < 2)) return D2PC_ERR_UNSUPPORTED;
   if (!(c->f == c->f) || c->f == 0.0) return D2PC_ERR_INVALID_ARGUMENT;
   return D2PC_OK;
 }

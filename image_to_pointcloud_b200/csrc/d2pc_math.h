@@ -123,6 +123,51 @@ D2PC_HD float bilinear_sample(const float *src, int32_t src_w, const AxisTap &tx
   return out;
 }
 
+// a1 for sources with a 1-pixel side.  OpenCV does not hand those to IPP: its own two-pass code runs
+// (imgproc resize.cpp, HResizeLinear / VResizeLinear) with float32 coordinates and weights, products
+// and sums rounded separately (no FMA), column weights clamped and a plain copy from the first column
+// with s + 1 >= w on, row weights NOT clamped (only the row indices are).
+struct GenericTap {
+  int32_t i0, i1;
+  float w0, w1;
+  int32_t copy;
+};
+D2PC_HD GenericTap generic_tap(int32_t d, double scale, int32_t n_src, int32_t is_column) {
+  GenericTap g;
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  float fl = floorf(f);
+  int32_t s = (int32_t)fl;
+  float t = f - fl;
+  g.copy = 0;
+  if (is_column) {
+    if (s < 0) { s = 0; t = 0.0f; }
+    if (s + 1 >= n_src) { g.copy = 1; s = s < n_src - 1 ? s : n_src - 1; t = 0.0f; }
+    g.i0 = s;
+    g.i1 = s + 1 < n_src ? s + 1 : n_src - 1;
+  } else {
+    g.i0 = s < 0 ? 0 : (s > n_src - 1 ? n_src - 1 : s);
+    g.i1 = s + 1 < 0 ? 0 : (s + 1 > n_src - 1 ? n_src - 1 : s + 1);
+  }
+  g.w0 = 1.0f - t;
+  g.w1 = t;
+  return g;
+}
+D2PC_HD float generic_blend(float a, float b, float w0, float w1) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
+#else
+  volatile float p = a * w0, q = b * w1;  // two rounded products, one rounded sum
+  return p + q;
+#endif
+}
+D2PC_HD float generic_sample(const float *src, int32_t src_w, const GenericTap &tx, const GenericTap &ty) {
+  const float *row0 = src + (size_t)ty.i0 * src_w, *row1 = src + (size_t)ty.i1 * src_w;
+  const float r0 = tx.copy ? row0[tx.i0] : generic_blend(row0[tx.i0], row0[tx.i1], tx.w0, tx.w1);
+  const float r1 = tx.copy ? row1[tx.i0] : generic_blend(row1[tx.i0], row1[tx.i1], tx.w0, tx.w1);
+  return generic_blend(r0, r1, ty.w0, ty.w1);
+}
+D2PC_HD bool resize_is_generic(int32_t src_h, int32_t src_w) { return src_h == 1 || src_w == 1; }
+
 // ---------------------------------------------------------------------------------------------
 // a3  np.percentile(d, [2, 98]), method "linear" (numpy 2.3.5 _quantile/_lerp; app.py:197)
 // ---------------------------------------------------------------------------------------------

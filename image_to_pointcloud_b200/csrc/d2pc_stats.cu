@@ -45,6 +45,21 @@ __global__ void taps_kernel(KParams kp) {
 }
 
 // ------------------------------------------------------------------------------------------
+// resize_generic_kernel: a1 for sources with a 1-pixel side (d2pc_math.h generic_sample), materialised
+// before the statistics; everything after it runs on the (H x W) map like a native-size input.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_generic_kernel(KParams kp) {
+  const uint32_t b = blockIdx.y;
+  const float *src = kp.depth + (size_t)b * kp.g.D;
+  float *dst = kp.resized + (size_t)b * kp.g.P;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < kp.g.P; p += gridDim.x * blockDim.x) {
+    const uint32_t v = p / (uint32_t)kp.g.W, u = p - v * (uint32_t)kp.g.W;
+    dst[p] = generic_sample(src, kp.g.w, generic_tap((int32_t)u, kp.g.scale_x, kp.g.w, 1),
+                            generic_tap((int32_t)v, kp.g.scale_y, kp.g.h, 0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // sample_kernel
 // ------------------------------------------------------------------------------------------
 template <bool NATIVE>
@@ -769,6 +784,13 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
   if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  if (!kp.g.native && resize_is_generic(kp.g.h, kp.g.w)) {
+    const uint32_t blocks = (kp.g.P + 255u) / 256u;
+    resize_generic_kernel<<<dim3(blocks < 148u * 8u ? blocks : 148u * 8u, cfg->batch), 256, 0, st>>>(kp);
+    D2PC_CHECK_LAUNCH();
+    kp = per_pixel_view(kp);   // the statistics read the materialised map
+    d_depth = kp.depth;
+  }
   const size_t sample_smem = (size_t)(4u << kSelBits) * sizeof(uint32_t);  // 64 KB
   const size_t select_smem = (size_t)(2u << kSelBits) * sizeof(uint32_t);  // 32 KB
   {

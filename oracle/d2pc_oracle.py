@@ -113,6 +113,8 @@ def resize_bilinear(depth: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     """
     src = np.ascontiguousarray(depth, dtype=F32)
     h, w = src.shape
+    if h == 1 or w == 1:
+        return _resize_bilinear_generic(src, out_h, out_w)
     x0, x1, tx, cx = _axis_taps(w, out_w)
     y0, y1, ty, cy = _axis_taps(h, out_h)
     with np.errstate(invalid="ignore", over="ignore"):
@@ -126,6 +128,49 @@ def resize_bilinear(depth: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
         # tap comes out as NaN (inf - inf); finite values are unchanged.
         corner = cy[:, None] & cx[None, :]
         out = np.where(corner & np.isinf(out), F32(np.nan), out)
+    return np.ascontiguousarray(out, dtype=F32)
+
+
+def _resize_bilinear_generic(src: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """``cv2.resize(..., INTER_LINEAR)`` for a float32 source with a 1-pixel side (same call site,
+    ``app.py:188``).  OpenCV 4.13.0 does not hand such sources to IPP; its own two-pass code runs
+    (third-party: opencv/modules/imgproc/src/resize.cpp, ``resizeGeneric_`` with ``HResizeLinear`` /
+    ``VResizeLinear``; not vendored in the reference, restated from the published source and pinned
+    against cv2.resize of this container, tests/test_oracle_golden.py):
+
+    * coordinates ``f = float32((d + 0.5) * scale - 0.5)``, ``s = floor(f)``, weight ``t = f - s`` in float32;
+    * columns: ``s < 0 -> s = 0, t = 0``; from the first column with ``s + 1 >= w`` on, a plain copy of
+      ``S[min(s, w - 1)]``; otherwise ``row = S[s] * (1 - t) + S[s + 1] * t`` (two products, one sum, each
+      rounded to float32, no FMA);
+    * rows: weights are NOT clamped, only the row indices are: ``out = R[clip(s)] * (1 - t) + R[clip(s + 1)] * t``
+      (so a one-row source gives ``v * (1 - t) + v * t``, and ``inf * 0`` is NaN where ``t == 0``).
+    """
+    h, w = src.shape
+
+    def coords(n_src, n_dst):
+        scale = F64(n_src) / F64(n_dst)
+        f = ((np.arange(n_dst, dtype=F64) + 0.5) * scale - 0.5).astype(F32)
+        s = np.floor(f).astype(np.int64)
+        t = (f - s.astype(F32)).astype(F32)
+        return s, t
+
+    sx, tx = coords(w, out_w)
+    low = sx < 0
+    sx = np.where(low, 0, sx)
+    tx = np.where(low, F32(0), tx)
+    copy = sx + 1 >= w                       # monotone in the column index: everything from xmax on
+    x0 = np.minimum(sx, w - 1)
+    x1 = np.minimum(sx + 1, w - 1)
+    sy, ty = coords(h, out_h)
+    y0 = np.clip(sy, 0, h - 1)
+    y1 = np.clip(sy + 1, 0, h - 1)
+    one = F32(1)
+    with np.errstate(invalid="ignore", over="ignore"):
+        a, b = src[:, x0], src[:, x1]
+        blend = ((a * (one - tx)[None, :]).astype(F32) + (b * tx[None, :]).astype(F32)).astype(F32)
+        rows = np.where(copy[None, :], a, blend)
+        r0, r1 = rows[y0, :], rows[y1, :]
+        out = ((r0 * (one - ty)[:, None]).astype(F32) + (r1 * ty[:, None]).astype(F32)).astype(F32)
     return np.ascontiguousarray(out, dtype=F32)
 
 

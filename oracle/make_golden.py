@@ -96,6 +96,15 @@ def small_cases():
     out["smooth_zeros"] = (img, np.full((24, 32), 3.0, np.float32), dict(density="high", smooth=True))
     d = np.full((24, 32), 3.0, np.float32); d[0, 0] = 1.0; d[5, 5] = 7.0
     out["smooth_minmax_f32"] = (img, d, dict(density="high", smooth=True))
+    # depth maps with a 1-pixel side: cv2.resize leaves IPP for OpenCV's own two-pass code (own random stream)
+    r1 = np.random.default_rng(4242)
+    out["src_1xN_up"] = (img, (r1.random((1, 11)) * 20).astype(np.float32), dict(density="high"))
+    out["src_Nx1_noinv"] = (img, (r1.random((37, 1)) * 20).astype(np.float32), dict(density="medium", invert=False))
+    out["src_1x1_resized"] = (img, np.array([[2.5]], np.float32), dict(density="high"))
+    d = (r1.standard_normal((1, 45)) * 5).astype(np.float32); d[0, 7] = np.inf; d[0, 30] = np.nan
+    out["src_1xN_nonfinite_down"] = (img_odd, d, dict(density="high"))
+    d = (r1.random((40, 1)) * 9).astype(np.float32); d[3, 0] = -np.inf
+    out["src_Nx1_nonfinite_low"] = (img_odd, d, dict(density="low"))
     return out
 
 

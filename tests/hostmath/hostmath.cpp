@@ -23,6 +23,13 @@ int hm_last_simple(void) { return g_last_simple; }
 
 int hm_resize(const float *src, int h, int w, float *dst, int H, int W) {
   const double sx = (double)w / (double)W, sy = (double)h / (double)H;
+  if (resize_is_generic(h, w)) {
+    for (int v = 0; v < H; ++v) {
+      GenericTap ty = generic_tap(v, sy, h, 0);
+      for (int u = 0; u < W; ++u) dst[(size_t)v * W + u] = generic_sample(src, w, generic_tap(u, sx, w, 1), ty);
+    }
+    return 0;
+  }
   for (int v = 0; v < H; ++v) {
     AxisTap ty = axis_tap(v, sy, h);
     for (int u = 0; u < W; ++u) {

@@ -55,8 +55,8 @@ def test_workspace_bytes_and_validation(lib):
     cfg.step = 3
     assert lib.d2pc_workspace_bytes(C.byref(cfg), C.byref(n)) == 1  # invalid argument
     cfg.step = 1
-    cfg.dep_h, cfg.dep_w = 1, 7  # needs a resize from a 1-pixel-high map: refused, not approximated
-    assert lib.d2pc_workspace_bytes(C.byref(cfg), C.byref(n)) == 4
+    cfg.dep_h, cfg.dep_w = 1, 7  # a 1-pixel-high map is a valid input (OpenCV's non-IPP resize arithmetic)
+    assert lib.d2pc_workspace_bytes(C.byref(cfg), C.byref(n)) == 0
     assert b"unsupported" in lib.d2pc_error_string(4)
     # NULL workspace / depth pointers are rejected before any launch
     cfg.dep_h, cfg.dep_w = 518, 686

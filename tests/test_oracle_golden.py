@@ -123,6 +123,24 @@ def test_resize_model_matches_cv2_here():
         assert O.count_bit_mismatch(a, b) == 0, (sh, dh)
 
 
+def test_resize_model_for_one_pixel_sides_matches_cv2_here():
+    """Sources with a 1-pixel side never reach IPP: OpenCV's own two-pass arithmetic (oracle
+    _resize_bilinear_generic), with non-finite values in the way."""
+    import cv2
+    rng = np.random.default_rng(16)
+    for t in range(120):
+        sh = (1, int(rng.integers(1, 120))) if t % 2 else (int(rng.integers(1, 120)), 1)
+        dh = (int(rng.integers(1, 160)), int(rng.integers(1, 160)))
+        if sh == dh:
+            continue
+        d = (rng.standard_normal(sh) * 3).astype(np.float32)
+        for _ in range(int(rng.integers(0, 3))):
+            d.flat[rng.integers(d.size)] = (np.inf, -np.inf, np.nan)[int(rng.integers(3))]
+        a = cv2.resize(d, (dh[1], dh[0]), interpolation=cv2.INTER_LINEAR)
+        b = O.resize_bilinear(d, dh[0], dh[1])
+        assert bool(np.all((a == b) | (np.isnan(a) & np.isnan(b)))), (sh, dh)
+
+
 def test_fmaf_exact():
     rng = np.random.default_rng(8)
     a = rng.standard_normal(200000).astype(np.float32)
