@@ -59,6 +59,16 @@ def _image_channels(image: np.ndarray) -> int:
     return 1
 
 
+def check_depth_dtype(depth: np.ndarray, img_h: int, img_w: int) -> None:
+    """The reference resizes the depth map in its own dtype (cv2.resize, app.py:188) and casts to float32
+    afterwards (app.py:191).  Only float32 maps (what run_depth_model returns, app.py:116) are interpolated
+    here; any other dtype is accepted when no resize is needed (the cast is then all that happens) and
+    refused otherwise instead of being interpolated in the wrong precision."""
+    if depth.dtype != np.float32 and tuple(depth.shape[:2]) != (img_h, img_w):
+        raise TypeError(f"depth of dtype {depth.dtype} needs a resize to {(img_h, img_w)}: pass float32 "
+                        "(the reference's depth model output, app.py:116) or a map of the image's size")
+
+
 def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
                          density: str = "medium",
                          invert: bool = True,
@@ -82,6 +92,7 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
         step = DENSITY_STEP[density]  # noqa: F841  (KeyError like the reference, before any work)
         if image.dtype != np.uint8:
             raise TypeError("image must be uint8 (cv2.imdecode output)")
+        check_depth_dtype(depth, int(img_h), int(img_w))
         img_c = _image_channels(image)
         eng = _engine_for(int(img_h), int(img_w), img_c, int(dep_h), int(dep_w), device)
         st = _STAGING[(str(eng.device), int(img_h), int(img_w), img_c, int(dep_h), int(dep_w))]
@@ -187,6 +198,8 @@ def depth_to_point_cloud_batch(images: Sequence[np.ndarray], depths: Sequence[np
     img_h, img_w = images[0].shape[:2]
     dep_h, dep_w = depths[0].shape[:2]
     img_c = _image_channels(images[0])
+    for d in depths:
+        check_depth_dtype(d, int(img_h), int(img_w))
     pipe = HostFramePipeline(img_h, img_w, dep_h, dep_w, img_c=img_c, chunk=min(chunk, len(images)),
                              density=density, invert=invert, depth_scale=depth_scale, fov=fov,
                              z_range=z_range, drop_nonfinite=drop_nonfinite, device=device)

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib, writers
 from ._lib import check
-from .api import _engine_for, _image_channels, _to_host, bounds_dict
+from .api import _engine_for, _image_channels, _to_host, bounds_dict, check_depth_dtype
 from .engine import DENSITY_STEP
 from .refine import statistical_outlier_removal
 
@@ -39,6 +39,7 @@ def point_cloud_stage(image: np.ndarray, depth: np.ndarray, *, density: str = "m
     lib = _lib.load_library()
     img_h, img_w = image.shape[:2]
     dep_h, dep_w = depth.shape[:2]
+    check_depth_dtype(depth, int(img_h), int(img_w))
     img_c = _image_channels(image)
     eng = _engine_for(int(img_h), int(img_w), img_c, int(dep_h), int(dep_w), device)
     dev = eng.device
