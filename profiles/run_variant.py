@@ -1,5 +1,5 @@
 """Runs one workload variant a few times (for ncu captures): python profiles/run_variant.py NAME [iters]
-NAME: native | dav2 | mask | mask4k | native4k | medium_dav2"""
+NAME: native | dav2 | mask | mask4k | native4k | medium_dav2 | scene_mask"""
 import os
 import sys
 
@@ -17,6 +17,7 @@ VARIANTS = {
     "medium_dav2": (1080, 1920, 518, 924, 16, None, "medium"),
     "mask4k_1": (2160, 3840, 2160, 3840, 1, (0.5, 9.5), "high"),
     "scene4k_1": (2160, 3840, 2160, 3840, 1, (0.5, 9.5), "high"),
+    "scene_mask": (1080, 1920, 1080, 1920, 16, (2.0, 6.0), "high"),   # coherent mask: whole tiles kept / dropped
 }
 
 

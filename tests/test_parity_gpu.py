@@ -217,6 +217,30 @@ def test_range_mask_and_compaction(m):
     assert_bits_equal(p, po[fin], "drop_nonfinite")
 
 
+def test_range_mask_with_whole_tiles_kept_or_dropped(m):
+    """Coherent masks: emit tiles (1024 consecutive rows) that keep nothing, everything (at 16-byte aligned and
+    at unaligned destinations) or a part, in every order."""
+    rng = np.random.default_rng(37)
+    H, W = 48, 1024   # one tile per image row
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    base = np.repeat(np.linspace(1.0, 19.0, H, dtype=np.float32)[:, None], W, axis=1)
+    base[::5] = 15.0                                     # rows jumping in and out of the range
+    dep = (base + rng.random((H, W)).astype(np.float32) * 0.01).astype(np.float32)
+    dep[7, :3] = 19.5; dep[20, 500] = 0.5; dep[33, 1023] = 19.9   # partial tiles shift the alignment of later ones
+    for inv in (True, False):
+        for zr in ((3.0, 7.0), (0.0, 10.0), (4.0, 4.5), (9.9, 10.0)):
+            po, co = _oracle(img, dep, density="high", invert=inv)
+            keep = O.range_mask(po, *zr)
+            p, c = m.depth_to_point_cloud(img, dep, density="high", invert=inv, z_range=zr)
+            assert len(p) == int(keep.sum()), (inv, zr)
+            assert_bits_equal(p, po[keep], f"tiles {inv} {zr} points")
+            assert_bits_equal(c, co[keep], f"tiles {inv} {zr} colors")
+            pb, cb, bnd = m.depth_to_point_cloud(img, dep, density="high", invert=inv, z_range=zr, return_bounds=True)
+            assert_bits_equal(pb, po[keep], "tiles + bounds")
+            if len(pb):
+                assert bnd["minX"] == float(pb[:, 0].min()) and bnd["maxZ"] == float(pb[:, 2].max())
+
+
 def test_voxel_downsample(m):
     rng = np.random.default_rng(36)
     H, W = 240, 320
