@@ -53,7 +53,7 @@ def _depth(rng, h, w, dist):
 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
-@given(H=st.integers(1, 70), W=st.integers(1, 90), h=st.integers(2, 60), w=st.integers(2, 80),
+@given(H=st.integers(1, 70), W=st.integers(1, 90), h=st.integers(1, 60), w=st.integers(1, 80),
        native=st.booleans(), dens=st.sampled_from(["low", "medium", "high"]), inv=st.booleans(),
        scale=st.sampled_from([10.0, 1.0, 3.7, 250.0]), dist=st.sampled_from(DISTS), chans=st.sampled_from([3, 3, 4, 1]),
        seed=st.integers(0, 2 ** 31 - 1))
