@@ -391,10 +391,21 @@ __device__ __forceinline__ float sor_filter(double kth) {
   return __double2float_ru(kth) * 1.000001f;
 }
 
+// The k smallest squared distances of one query, ascending.  STRIDE 1: a per-thread local array; STRIDE
+// kSorThreads: one column of a [k][kSorThreads] shared-memory array (k <= kSorSharedK) -- the insertion loop is a
+// chain of dependent loads and stores, and local memory competes with the candidate stream for L1.
+template <int STRIDE>
+struct KBest {
+  double *p;
+  __device__ __forceinline__ double &operator[](int t) const { return p[t * STRIDE]; }
+};
+constexpr int kSorSharedK = 24;
+
 // Candidates of one cell.  A float32 estimate of the squared distance (relative error < 4e-7) rejects most
 // candidates for a sixth of the cost; whatever passes the (conservative) filter is evaluated exactly.
+template <class B>
 __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, const double q[3], const float qf[3],
-                                               double *best, int k, float &thrf) {
+                                               const B &best, int k, float &thrf, double &kth) {
   const uint32_t s = w.cell_off[cell], e = w.cell_off[cell + 1];
   constexpr int U = 4;  // candidates in flight per iteration (independent loads and float32 estimates)
   if (w.cell_cnt[cell] & kSorSortedFlag) {
@@ -408,7 +419,7 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
     uint32_t r = lo;   // next candidate to the right
     uint32_t l = lo;   // next candidate to the left is l - 1
     bool go_r = r < e, go_l = l > s;
-    while ((go_r || go_l) && best[k - 1] > 0.0) {  // k coincident points: nothing can be closer
+    while ((go_r || go_l) && kth > 0.0) {  // k coincident points: nothing can be closer
       float p[2 * U][3];
       bool ok[2 * U];
 #pragma unroll
@@ -432,11 +443,12 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
           double d2 = dx * dx;
           d2 += dy * dy;
           d2 += dz * dz;
-          if (d2 < best[k - 1]) {
+          if (d2 < kth) {
             int t = k - 1;
             while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
             best[t] = d2;
-            thrf = sor_filter(best[k - 1]);
+            kth = best[k - 1];
+            thrf = sor_filter(kth);
           }
         }
       }
@@ -445,7 +457,7 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
     }
     return;
   }
-  for (uint32_t j0 = s; j0 < e && best[k - 1] > 0.0; j0 += U) {  // (k coincident points end the search)
+  for (uint32_t j0 = s; j0 < e && kth > 0.0; j0 += U) {  // (k coincident points end the search)
     float p[U][3], d2f[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -465,34 +477,40 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
       double d2 = dx * dx;   // nanoflann L2_Simple: result += diff * diff, axis by axis (no contraction: --fmad=false)
       d2 += dy * dy;
       d2 += dz * dz;
-      if (d2 < best[k - 1]) {
+      if (d2 < kth) {
         int t = k - 1;
         while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
         best[t] = d2;
-        thrf = sor_filter(best[k - 1]);
+        kth = best[k - 1];
+        thrf = sor_filter(kth);
       }
     }
   }
 }
 
 // a neighbour cell by key: one hash probe; most cells of a shell do not exist
+template <class B>
 __device__ __forceinline__ void sor_visit_key(const SorWs &w, unsigned long long key, const double q[3], const float qf[3],
-                                              double *best, int k, float &thrf) {
+                                              const B &best, int k, float &thrf, double &kth) {
   uint32_t slot;
-  if (sor_find(w, key, &slot)) sor_visit_cell(w, slot, q, qf, best, k, thrf);
+  if (sor_find(w, key, &slot)) sor_visit_cell(w, slot, q, qf, best, k, thrf, kth);
 }
 
 // Queries run in CELL order (thread j owns the j-th sorted point): the lanes of a warp then share their
 // query cell, walk the same candidate lists with the same trip counts and read the same addresses.
+template <bool SHARED>
 __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int nb_neighbors) {
+  extern __shared__ double s_best[];   // SHARED: [k][kSorThreads]
   const SorHeader *h = w.hdr;
   const uint32_t n = h->n;
   const uint32_t j = blockIdx.x * (uint32_t)kSorThreads + threadIdx.x;
   if (j >= n) return;
   const uint32_t i = w.sorted_idx[j];
   const int k = (int)min((uint32_t)nb_neighbors, n);
-  double best[kSorMaxK];
+  double loc[SHARED ? 1 : kSorMaxK];
+  const KBest<SHARED ? kSorThreads : 1> best{SHARED ? s_best + threadIdx.x : loc};
   for (int t = 0; t < k; ++t) best[t] = __longlong_as_double(0x7FF0000000000000ll);
+  double kth = __longlong_as_double(0x7FF0000000000000ll);
   const float qf[3] = {w.sorted[3 * (size_t)j], w.sorted[3 * (size_t)j + 1], w.sorted[3 * (size_t)j + 2]};
   const double q[3] = {(double)qf[0], (double)qf[1], (double)qf[2]};
   float thrf = __int_as_float(0x7F800000);
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int 
     dhi[a] = fmax(lo + h->h - q[a], 0.0);
     rmax = max(rmax, max(c[a], h->dim[a] - 1 - c[a]));
   }
-  sor_visit_cell(w, cell, q, qf, best, k, thrf);
+  sor_visit_cell(w, cell, q, qf, best, k, thrf, kth);
   const int32_t dim[3] = {nx, ny, nz};
   for (int32_t R = 1; R <= rmax; ++R) {
     // Unvisited points lie beyond a face of the block of radius R - 1 that is still inside the grid:
@@ -525,7 +543,7 @@ __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int 
       if (c[a] + R <= dim[a] - 1) reach = fmin(reach, (double)(R - 1) * h->h + dhi[a]);
     }
     reach -= h->slack;
-    if ((reach > 0.0 && best[k - 1] <= reach * reach) || best[k - 1] == 0.0) break;
+    if ((reach > 0.0 && kth <= reach * reach) || kth == 0.0) break;
     // shell of Chebyshev radius R, clipped to the grid, as six slabs (no cell is visited twice):
     //   x faces: a0 = c0 -+ R, full (a1, a2) range;  y faces: a1 = c1 -+ R, a0 interior;  z faces: a0, a1 interior
     const int32_t x0 = max(c0 - R, 0), x1 = min(c0 + R, nx - 1);
@@ -537,19 +555,19 @@ __global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int 
       const int32_t a0 = side ? c0 + R : c0 - R;
       if (a0 < 0 || a0 >= nx) continue;
       for (int32_t a1 = y0; a1 <= y1; ++a1)
-        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf);
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf, kth);
     }
     for (int side = 0; side < 2; ++side) {
       const int32_t a1 = side ? c1 + R : c1 - R;
       if (a1 < 0 || a1 >= ny) continue;
       for (int32_t a0 = xi0; a0 <= xi1; ++a0)
-        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf);
+        for (int32_t a2 = z0; a2 <= z1; ++a2) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf, kth);
     }
     for (int side = 0; side < 2; ++side) {
       const int32_t a2 = side ? c2 + R : c2 - R;
       if (a2 < 0 || a2 >= nz) continue;
       for (int32_t a0 = xi0; a0 <= xi1; ++a0)
-        for (int32_t a1 = yi0; a1 <= yi1; ++a1) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf);
+        for (int32_t a1 = yi0; a1 <= yi1; ++a1) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf, kth);
     }
   }
   double s = 0.0;
@@ -700,7 +718,12 @@ extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const ui
   D2PC_CHECK_LAUNCH();
   sor_heavy_sort_kernel<<<kSorMaxHeavy, 1024, 0, st>>>(w);
   D2PC_CHECK_LAUNCH();
-  sor_query_kernel<<<row_blocks, kSorThreads, 0, st>>>(w, nb_neighbors);
+  if (nb_neighbors <= kSorSharedK) {
+    const size_t smem = (size_t)nb_neighbors * kSorThreads * sizeof(double);   // <= 48 KB
+    sor_query_kernel<true><<<row_blocks, kSorThreads, smem, st>>>(w, nb_neighbors);
+  } else {
+    sor_query_kernel<false><<<row_blocks, kSorThreads, 0, st>>>(w, nb_neighbors);
+  }
   D2PC_CHECK_LAUNCH();
   double *partial = reinterpret_cast<double *>(w.blk_sum);  // the cell scan is done with it
   for (int pass = 0; pass < 2; ++pass) {
