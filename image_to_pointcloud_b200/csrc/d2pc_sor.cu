@@ -499,7 +499,7 @@ __device__ __forceinline__ void sor_visit_key(const SorWs &w, unsigned long long
 // Queries run in CELL order (thread j owns the j-th sorted point): the lanes of a warp then share their
 // query cell, walk the same candidate lists with the same trip counts and read the same addresses.
 template <bool SHARED>
-__global__ void __launch_bounds__(kSorThreads, 3) sor_query_kernel(SorWs w, int nb_neighbors) {
+__global__ void __launch_bounds__(kSorThreads, 4) sor_query_kernel(SorWs w, int nb_neighbors) {
   extern __shared__ double s_best[];   // SHARED: [k][kSorThreads]
   const SorHeader *h = w.hdr;
   const uint32_t n = h->n;
