@@ -108,8 +108,28 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
             if img_c >= 3:
                 st["bgr_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(image)))
                 st["bgr_dev"].copy_(st["bgr_pin"], non_blocking=True)
+            # Without a mask every grid point is emitted: the row count is known, so the device -> host copies
+            # are enqueued behind the emit and the call synchronises once.
+            plain = z_range is None and not drop_nonfinite and not want_voxel
+            host = {}
+
+            def copy_out(xyz, rgb, count, bounds):
+                for key, t in (("xyz", xyz), ("rgb", rgb)):
+                    if key not in host:
+                        host[key] = torch.empty(t.shape[1:], dtype=t.dtype, pin_memory=True)
+                    host[key].copy_(t[0], non_blocking=True)
+                if bounds is not None:
+                    if "bounds" not in host:
+                        host["bounds"] = torch.empty((6,), dtype=torch.float32, pin_memory=True)
+                    host["bounds"].copy_(bounds[0], non_blocking=True)
+
             res = eng.process(cfg, st["depth_dev"], st["bgr_dev"], stream=stream,
-                              smooth_ksize=(smooth_ksize if smooth else None))
+                              smooth_ksize=(smooth_ksize if smooth else None), after_emit=copy_out if plain else None)
+            if plain:   # process() has synchronised the stream
+                out = (host["xyz"].numpy(), host["rgb"].numpy())
+                if return_bounds:
+                    out = out + (bounds_dict(host["bounds"].numpy()),)
+                return out
             if want_voxel:
                 vxyz, vrgb, vidx, vcount = eng.voxel_downsample(cfg, res, float(voxel_size),
                                                                 want_index=return_voxel_index, stream=stream)

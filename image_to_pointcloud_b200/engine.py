@@ -230,9 +230,11 @@ class FrameEngine:
     # ---- whole path ----------------------------------------------------------------------
     def process(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],
                 xyz: Optional[torch.Tensor] = None, rgb: Optional[torch.Tensor] = None,
-                count: Optional[torch.Tensor] = None, stream=None, smooth_ksize=None) -> EmitResult:
+                count: Optional[torch.Tensor] = None, stream=None, smooth_ksize=None, after_emit=None) -> EmitResult:
         """stats -> emit for one device-resident batch; synchronises the stream once to learn
-        whether any frame needs the exact fallback, and if so runs it and re-emits those frames."""
+        whether any frame needs the exact fallback, and if so runs it and re-emits those frames.
+        ``after_emit(xyz, rgb, count, bounds)`` is called after every emit has been enqueued and before the
+        stream is synchronised (device -> host copies that should ride on the same synchronisation)."""
         self._check_inputs(depth, bgr)
         if xyz is None or rgb is None:
             xyz, rgb = self.alloc_outputs(cfg)
@@ -249,6 +251,9 @@ class FrameEngine:
                 self.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, bounds, s)
             else:
                 self.enqueue_emit_smooth(cfg, smooth_ksize, depth, bgr, xyz, rgb, count, bounds, s)
+            if after_emit is not None:
+                with torch.cuda.stream(s):
+                    after_emit(xyz, rgb, count, bounds)
         self.enqueue_stats(cfg, depth, s)
         self.enqueue_status(cfg, s)
         emit()
