@@ -1,0 +1,105 @@
+"""Randomised check of rows f1 (statistical outlier removal) and ax-2 (voxel grid) against the oracle:
+python profiles/fuzz_rows.py [examples] [seed].  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import image_to_pointcloud_b200 as m  # noqa: E402
+from oracle import d2pc_oracle as O  # noqa: E402  (checker only)
+
+
+def cloud(rng, n, kind):
+    if kind == "uniform":
+        p = rng.random((n, 3)) * rng.choice([1.0, 10.0, 1e3])
+    elif kind == "clusters":
+        c = rng.random((max(1, n // 200), 3)) * 10
+        p = c[rng.integers(len(c), size=n)] + rng.standard_normal((n, 3)) * 0.05
+    elif kind == "plane":
+        p = np.c_[rng.random((n, 2)) * 5, np.full(n, 2.0) + rng.standard_normal(n) * 1e-4]
+    elif kind == "line":
+        t = rng.random(n)
+        p = np.c_[t * 7, t * -3 + 1, t * 0.5]
+    elif kind == "duplicates":
+        base = rng.random((max(1, n // 7), 3))
+        p = base[rng.integers(len(base), size=n)]
+    elif kind == "outliers":
+        p = rng.standard_normal((n, 3))
+        k = max(1, n // 50)
+        p[rng.choice(n, k, replace=False)] += rng.standard_normal((k, 3)) * 100
+    else:  # lattice: heavy ties in the distances
+        g = int(np.ceil(n ** (1 / 3)))
+        p = np.stack(np.meshgrid(*[np.arange(g)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] * 0.25
+    return np.ascontiguousarray(p, dtype=np.float32)
+
+
+KINDS = ["uniform", "clusters", "plane", "line", "duplicates", "outliers", "lattice"]
+
+
+def main():
+    n_ex = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 99
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    sor = {"examples": 0, "index_sets_identical": 0, "differ_only_at_threshold": 0, "mismatches": 0, "points": 0}
+    vox = {"examples": 0, "mismatches": 0, "points": 0, "max_mean_abs_err": 0.0}
+    bad = []
+    for it in range(n_ex):
+        n = int(rng.choice([1, 2, 5, 19, 20, 21, 100, 1000, 5000, 20000, 60000]))
+        kind = KINDS[int(rng.integers(len(KINDS)))]
+        p = cloud(rng, n, kind)
+        c = rng.integers(0, 256, (n, 3)).astype(np.float32)
+        k = int(rng.choice([1, 2, 5, 10, 20, 20, 20, 24, 25, 40, 64]))
+        ratio = float(rng.choice([0.5, 1.0, 2.0, 2.0, 3.0]))
+        keep, avg, (mean, std, thr) = O.statistical_outlier_removal(p, k, ratio)
+        gp, gc, gidx, st = m.statistical_outlier_removal(p, c, k, ratio)
+        sor["examples"] += 1
+        sor["points"] += n
+        if np.isnan(thr):
+            ok = len(gidx) == 0 and len(keep) == 0
+            sor["index_sets_identical"] += ok
+        else:
+            diff = set(keep.tolist()).symmetric_difference(set(gidx.tolist()))
+            border = np.abs(avg - thr) <= 1e-9 * abs(thr)
+            ok = all(border[i] for i in diff) and abs(st["threshold"] - thr) <= 1e-11 * abs(thr)
+            if ok and not diff:
+                ok = np.array_equal(gidx, keep) and np.array_equal(gp, p[keep]) and np.array_equal(gc, c[keep])
+                sor["index_sets_identical"] += ok
+            elif ok:
+                sor["differ_only_at_threshold"] += 1
+        if not ok:
+            sor["mismatches"] += 1
+            bad.append(dict(row="f1", it=it, n=n, kind=kind, k=k, ratio=ratio))
+        # ax-2 through the public API needs an image: use the SOR clouds as emitted rows of a synthetic frame instead
+        if n >= 100 and it % 3 == 0:
+            H, W = 60 + int(rng.integers(100)), 80 + int(rng.integers(120))
+            img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+            dep = (rng.random((H, W)) * 20).astype(np.float32) if it % 2 else \
+                (10 + np.add.outer(np.arange(H), np.arange(W)) * 0.01 + rng.random((H, W)) * 0.05).astype(np.float32)
+            vs = float(rng.choice([0.005, 0.02, 0.1, 0.5]))
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                po, co = O.depth_to_point_cloud(img, dep, density="high")
+            vp, vc, vidx = O.voxel_downsample(po, co, vs)
+            gvp, gvc, gvi = m.depth_to_point_cloud(img, dep, density="high", voxel_size=vs, return_voxel_index=True)
+            key = lambda i: (i[:, 0].astype(np.int64) << 42) | (i[:, 1].astype(np.int64) << 21) | i[:, 2]
+            order = np.argsort(key(gvi), kind="stable")
+            okv = len(gvp) == len(vp) and np.array_equal(gvi[order], vidx) and \
+                np.allclose(gvp[order], vp, rtol=1e-5, atol=1e-6) and np.allclose(gvc[order], vc, rtol=1e-6, atol=0)
+            vox["examples"] += 1
+            vox["points"] += len(po)
+            if okv:
+                vox["max_mean_abs_err"] = max(vox["max_mean_abs_err"], float(np.abs(gvp[order] - vp).max()))
+            else:
+                vox["mismatches"] += 1
+                bad.append(dict(row="ax-2", it=it, H=H, W=W, voxel_size=vs))
+    print(json.dumps({"seed": seed, "f1_sor": sor, "ax2_voxel": vox, "seconds": round(time.time() - t0, 1), "first_bad": bad[:6]}))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
