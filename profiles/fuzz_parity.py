@@ -1,4 +1,4 @@
-"""Randomised parity run against the oracle (bit-exact): python profiles/fuzz_parity.py [examples] [seed]
+"""Randomised parity run against the oracle (bit-exact): python profiles/fuzz_parity.py [examples] [seed] [big]
 Shapes up to 300 x 420 (depth maps down to 1-pixel sides), every density / invert / depth_scale / fov, seven value
 distributions, 1/3/4-channel images, optional depth-range mask and drop_nonfinite.  Prints one JSON line."""
 import json
@@ -18,15 +18,18 @@ from tests.test_property_gpu import DISTS, _depth  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 2026
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"   # frames of 0.2 - 2.4 Mpixel: sampled statistics, many tiles
     rng = np.random.default_rng(seed)
     bad, points, t0 = [], 0, time.time()
     stats = {"resized": 0, "one_pixel_side": 0, "masked": 0, "nonfinite": 0, "empty_result": 0}
     for it in range(n):
-        H, W = int(rng.integers(1, 300)), int(rng.integers(1, 420))
+        H, W = (int(rng.integers(400, 1200)), int(rng.integers(500, 2000))) if big else \
+            (int(rng.integers(1, 300)), int(rng.integers(1, 420)))
         if rng.random() < 0.35:
             h, w = H, W
         else:
-            h, w = int(rng.integers(1, 260)), int(rng.integers(1, 360))
+            h, w = (int(rng.integers(200, 1300)), int(rng.integers(200, 2100))) if big else \
+                (int(rng.integers(1, 260)), int(rng.integers(1, 360)))
             if rng.random() < 0.1:
                 h = 1
             elif rng.random() < 0.1:
