@@ -100,3 +100,34 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_plain_c_host_compiles_links_and_agrees_with_ctypes(lib, tmp_path):
+    """include/d2pc.h is a C header (C99, -pedantic clean); a C host linked against libd2pc.so gets the same
+    sizes and codes as the ctypes binding."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "host_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_host", "host_check.c"), "-o", exe, "-L", libdir, "-ld2pc",
+           "-Wl,-rpath," + libdir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = dict(line.split(" ", 1) for line in out.strip().splitlines())
+    cfg = m.D2pcConfig(batch=2, img_h=480, img_w=640, img_c=3, dep_h=518, dep_w=686, step=1, invert=1,
+                       depth_scale=10.0, cx=320.0, cy=240.0, f=768.0)
+    n = C.c_size_t(0)
+    assert int(got["abi_version"]) == lib.d2pc_abi_version()
+    assert int(got["sizeof_config"]) == C.sizeof(m.D2pcConfig)
+    assert int(got["sizeof_frame_params"]) == C.sizeof(m.D2pcFrameParams)
+    assert lib.d2pc_workspace_bytes(C.byref(cfg), C.byref(n)) == 0 and int(got["workspace_bytes"]) == n.value
+    assert lib.d2pc_voxel_table_bytes(C.byref(cfg), C.byref(n)) == 0 and int(got["voxel_table_bytes"]) == n.value
+    assert lib.d2pc_smooth_scratch_bytes(C.byref(cfg), C.byref(n)) == 0 and int(got["smooth_bytes"]) == n.value
+    assert lib.d2pc_sor_scratch_bytes(100000, C.byref(n)) == 0 and int(got["sor_bytes"]) == n.value
+    assert lib.d2pc_xyz_text_scratch_bytes(100000, C.byref(n)) == 0 and int(got["text_bytes"]) == n.value
+    assert [got[k] for k in ("workspace_rc", "voxel_table_rc", "smooth_rc", "sor_rc", "text_rc")] == ["0"] * 5
+    assert got["bad_step_rc"] == "1" and got["null_rc"] == "1" and got["err1"] == "invalid argument"
