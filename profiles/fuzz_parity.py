@@ -15,10 +15,11 @@ from oracle import d2pc_oracle as O  # noqa: E402  (checker only)
 from tests.test_property_gpu import DISTS, _depth  # noqa: E402
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 2026
-    big = len(sys.argv) > 3 and sys.argv[3] == "big"   # frames of 0.2 - 2.4 Mpixel: sampled statistics, many tiles
+def main(argv=None):
+    argv = list(sys.argv if argv is None else argv)
+    n = int(argv[1]) if len(argv) > 1 else 1000
+    seed = int(argv[2]) if len(argv) > 2 else 2026
+    big = len(argv) > 3 and argv[3] == "big"   # frames of 0.2 - 2.4 Mpixel: sampled statistics, many tiles
     rng = np.random.default_rng(seed)
     bad, points, t0 = [], 0, time.time()
     stats = {"resized": 0, "one_pixel_side": 0, "masked": 0, "nonfinite": 0, "empty_result": 0}

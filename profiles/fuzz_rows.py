@@ -40,9 +40,10 @@ def cloud(rng, n, kind):
 KINDS = ["uniform", "clusters", "plane", "line", "duplicates", "outliers", "lattice"]
 
 
-def main():
-    n_ex = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 99
+def main(argv=None):
+    argv = list(sys.argv if argv is None else argv)
+    n_ex = int(argv[1]) if len(argv) > 1 else 300
+    seed = int(argv[2]) if len(argv) > 2 else 99
     rng = np.random.default_rng(seed)
     t0 = time.time()
     sor = {"examples": 0, "index_sets_identical": 0, "differ_only_at_threshold": 0, "mismatches": 0, "points": 0}

@@ -20,9 +20,10 @@ def oracle(img, dep, **kw):
         return O.depth_to_point_cloud(img, dep, **kw)
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+def main(argv=None):
+    argv = list(sys.argv if argv is None else argv)
+    n = int(argv[1]) if len(argv) > 1 else 300
+    seed = int(argv[2]) if len(argv) > 2 else 8
     rng = np.random.default_rng(seed)
     t0 = time.time()
     sm = {"examples": 0, "bit_exact": 0, "within_1e-5": 0, "mismatches": 0}

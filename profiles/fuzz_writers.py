@@ -29,9 +29,10 @@ def rows(rng, n, kind):
     return np.ascontiguousarray(v, dtype=np.float32), c
 
 
-def main():
-    runs = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+def main(argv=None):
+    argv = list(sys.argv if argv is None else argv)
+    runs = int(argv[1]) if len(argv) > 1 else 40
+    seed = int(argv[2]) if len(argv) > 2 else 5
     rng = np.random.default_rng(seed)
     t0 = time.time()
     res = {"xyz_text": [0, 0], "las": [0, 0], "ply": [0, 0], "preview": [0, 0]}   # [runs, mismatches]
