@@ -32,7 +32,9 @@ def main(argv=None):
     for it in range(n):
         H, W = int(rng.integers(1, 200)), int(rng.integers(1, 280))
         native = rng.random() < 0.4
-        h, w = (H, W) if native else (int(rng.integers(2, 160)), int(rng.integers(2, 220)))
+        h, w = (H, W) if native else (int(rng.integers(1, 160)), int(rng.integers(1, 220)))
+        if not native and rng.random() < 0.1:   # depth maps with a 1-pixel side (OpenCV's non-IPP resize)
+            h, w = (1, w) if rng.random() < 0.5 else (h, 1)
         img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
         dist = DISTS[int(rng.integers(len(DISTS)))]
         dep = _depth(rng, h, w, dist)
