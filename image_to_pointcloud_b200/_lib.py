@@ -11,6 +11,7 @@ D2PC_ABI_VERSION = 1
 D2PC_OK = 0
 FRAME_PENDING, FRAME_READY, FRAME_NEEDS_FALLBACK = 0, 1, 2
 BRANCH_PCT, BRANCH_MINMAX, BRANCH_ZEROS = 0, 1, 2
+PATH_GRAPH, PATH_NO_OVERLAP, PATH_NO_L2_HINTS, PATH_STREAMS = 1, 2, 4, 8
 
 EXPORTS = [
     "d2pc_abi_version", "d2pc_error_string", "d2pc_last_cuda_error", "d2pc_workspace_bytes",
@@ -19,6 +20,7 @@ EXPORTS = [
     "d2pc_preview_enqueue", "d2pc_voxel_table_bytes", "d2pc_voxel_table_init", "d2pc_voxel_enqueue",
     "d2pc_preview_rows_enqueue", "d2pc_xyz_text_scratch_bytes", "d2pc_xyz_text_measure_enqueue",
     "d2pc_xyz_text_write_enqueue", "d2pc_rows_bounds_enqueue", "d2pc_las_records_enqueue", "d2pc_ply_records_enqueue", "d2pc_sor_scratch_bytes", "d2pc_sor_enqueue",
+    "d2pc_path_create", "d2pc_path_destroy", "d2pc_path_enqueue", "d2pc_path_trace_offset",
 ]
 
 
@@ -92,9 +94,15 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.d2pc_ply_records_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, vp]
     lib.d2pc_sor_scratch_bytes.argtypes = [C.c_uint32, C.POINTER(C.c_size_t)]
     lib.d2pc_sor_enqueue.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_int32, C.c_double, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
+    lib.d2pc_path_trace_offset.argtypes = [cfgp, C.POINTER(C.c_size_t)]
+    lib.d2pc_path_create.argtypes = [C.POINTER(vp)]
+    lib.d2pc_path_destroy.argtypes = [vp]
+    lib.d2pc_path_destroy.restype = None
+    lib.d2pc_path_enqueue.argtypes = [vp, cfgp, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32,
+                                      C.c_int32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("d2pc_error_string", "d2pc_last_cuda_error"):
+        if name not in ("d2pc_error_string", "d2pc_last_cuda_error", "d2pc_path_destroy"):
             fn.restype = C.c_int
     if lib.d2pc_abi_version() != D2PC_ABI_VERSION:
         raise RuntimeError("libd2pc.so ABI version mismatch")

@@ -14,8 +14,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libd2pc.so")
-SOURCES = ["d2pc_api.cu", "d2pc_stats.cu", "d2pc_emit.cu", "d2pc_voxel.cu", "d2pc_serialise.cu", "d2pc_sor.cu"]
-HEADERS = ["d2pc_math.h", "d2pc_format.h", "d2pc_device.cuh", os.path.join("..", "..", "include", "d2pc.h")]
+SOURCES = ["d2pc_api.cu", "d2pc_stats.cu", "d2pc_emit.cu", "d2pc_path.cu", "d2pc_voxel.cu", "d2pc_serialise.cu", "d2pc_sor.cu"]
+HEADERS = ["d2pc_math.h", "d2pc_format.h", "d2pc_device.cuh", "d2pc_stats_dev.cuh", "d2pc_emit_dev.cuh", os.path.join("..", "..", "include", "d2pc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -48,13 +48,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
         if open(stamp).read().strip() == digest:
             return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    # one nvcc per translation unit, in parallel, then one link step
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(BUILD_DIR, os.path.splitext(src)[0] + ".o")
+        res = subprocess.run([nvcc] + compile_flags + ["-c", os.path.join(CSRC, src), "-o", obj],
+                             capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for src, _, res in results:
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a"] +
+                         [obj for _, obj, _ in results] + ["-o", LIB_PATH], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB_PATH

@@ -20,7 +20,8 @@ constexpr int kSelBits = 12;           // bucket histogram levels of the exact s
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 32;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // 4096 pixels per CTA
-constexpr int kSelThreads = 1024;
+constexpr int kSelThreads = 1024;      // sample kernel
+constexpr int kSelectThreads = 512;    // stand-alone select kernel
 constexpr int kEmitThreads = 256;
 constexpr int kEmitPerThread = 4;
 constexpr int kEmitTile = kEmitThreads * kEmitPerThread;  // 1024 output points per CTA
@@ -62,18 +63,20 @@ struct __align__(256) FrameState {
   uint32_t brL[2], brU[2];
   uint32_t sample_ok;     // 0: sample saw a non-finite value
   // streaming pass results (atomically accumulated by scan CTAs)
-  uint32_t below[2];      // finite keys <  brL
+  uint32_t below[2];      // [0]: finite values < brL[0] (counted by the scan); [1]: derived by select
+  uint32_t above1;        // finite values > brU[1] (counted by the scan)
   uint32_t eqL[2];        // finite keys == brL
   uint32_t inside[2];     // finite keys strictly inside (brL, brU); appended to the candidate list
   uint32_t eqU[2];        // finite keys == brU (brU != brL)
   uint32_t n_nonfinite, n_nan;
-  uint32_t nqueue[2];     // values the scan deferred to the bracket's raw queue (inside it; non-finite -> queue 0)
+  // values the scan deferred to the two raw queues; reserved as ONE 64-bit atomic (low word queue 0, high word
+  // queue 1): same-line atomics serialise in L2 at ~16 ns each, and a frame has hundreds of scan tiles
+  alignas(8) uint32_t nqueue[2];
   uint32_t min_key, max_key;  // of the repaired map (fallback path only)
   // exact selection
   uint32_t sel_key[4];    // keys at ranks lo2, hi2, lo98, hi98
   uint32_t sel_fail;
   uint32_t sel_done;      // bracket CTAs finished (0..2)
-  int32_t status;         // D2PC_FRAME_*
   // fallback radix select
   uint32_t fb_prefix[kFbTargets];
   uint32_t fb_rank[kFbTargets];
@@ -84,8 +87,29 @@ struct __align__(256) FrameState {
   float mask_lo, mask_hi;
   uint32_t emit_count;
   uint32_t bounds_min[3], bounds_max[3];  // ordered keys of kept x, y, z
-  // parameters consumed by emit
-  NormParams norm;
+  // What the emit consumes, in ONE 128-byte line: the persistent path kernel takes a snapshot of it with a single
+  // warp-wide load (status is written last, after a fence: a snapshot that shows READY shows the final norm).
+  alignas(128) NormParams norm;
+  int32_t status;         // D2PC_FRAME_*
+};
+static_assert(sizeof(NormParams) + 4 <= 128, "norm + status must share one 128-byte line");
+constexpr int kStatusWord = (int)(sizeof(NormParams) / 4);  // index of `status` in the line's 32 words
+
+// Per-frame scratch of the cooperative selection inside the persistent path kernel (several CTAs per bracket):
+// global bucket histograms, classification counts, the located buckets and their members.  Zeroed per step by
+// the sample kernel.
+constexpr uint32_t kSelBins = 4096, kSelListCap = 1024;
+struct __align__(256) SelShared {
+  uint32_t counts[2][8];     // below, eqL, inside, eqU, non-finite, NaN
+  uint32_t scan_done;        // scan tiles finished (the selection waits for all of them); on this line, not on
+                             // the FrameState line the scan's reservations hammer
+  uint32_t a_done[2], c_done[2];
+  uint32_t bin_ready[2];     // 0 pending, 1 members wanted, 2 bracket finished without a collect
+  uint32_t bin[2][2], base[2][2], need[2][2], want[2][2], shared_bin[2], key[2][2];
+  uint32_t mcount[2][2], mmin[2][2], mmax[2][2];   // mmin holds ~min (zero-initialised scratch)
+  uint32_t pad_[7];           // header = 64 words: members / hist stay 16-byte aligned
+  uint32_t members[2][2][kSelListCap];
+  uint32_t hist[2][kSelBins];
 };
 
 // One bilinear tap of the IPP model (d2pc_math.h axis_tap), 8 bytes, precomputed per call for
@@ -95,8 +119,13 @@ struct __align__(8) TapEntry {
   float t;      // float32 weight of tap 1
 };
 
+// scheduler words of the persistent path kernel: kSchedQueues work counters, one per 128-byte line, then the abort
+// flag on its own line; the per-frame trace follows
+constexpr int kSchedQueues = 32;
+constexpr size_t kSchedBytes = 128 * (kSchedQueues + 1);
+
 struct WsLayout {
-  size_t state_off, cand_off, tile_off, fbhist_off, tap_off, resized_off, total;
+  size_t state_off, cand_off, tile_off, fbhist_off, tap_off, sched_off, sel_off, resized_off, total;
   uint32_t cand_cap;      // keys per (frame, bracket)
   uint32_t emit_tiles;    // emit CTAs per frame
 };
@@ -118,6 +147,9 @@ inline WsLayout make_layout(const D2pcConfig &c) {
   L.tile_off = off;   off = align_up(off + (size_t)c.batch * L.emit_tiles * sizeof(unsigned long long), 256);
   L.fbhist_off = off; off = align_up(off + (size_t)c.batch * kFbTargets * 256 * sizeof(uint32_t), 256);
   L.tap_off = off;    off = align_up(off + ((size_t)c.img_w + (size_t)c.img_h) * sizeof(TapEntry), 256);
+  // work counter and abort flag of the persistent path kernel, then 8 timestamps per frame (its trace)
+  L.sched_off = off;  off = align_up(off + kSchedBytes + (size_t)c.batch * 64, 256);
+  L.sel_off = off;    off = align_up(off + (size_t)c.batch * sizeof(SelShared), 256);
   // resized depth only: the scan materialises the (H x W) map once; every later kernel reads it
   L.resized_off = off;
   if (!g.native) off = align_up(off + (size_t)c.batch * g.P * sizeof(float), 256);
@@ -135,10 +167,21 @@ struct KParams {
   unsigned long long *tile_state;  // [batch][emit_tiles]
   uint32_t *fb_hist;        // [batch][kFbTargets][256]
   const TapEntry *xtab, *ytab;  // [W], [H] bilinear taps (resized depth only)
+  SelShared *sel;           // [batch] cooperative-selection scratch (persistent path kernel)
+  uint32_t *sched;          // scheduler words of the persistent path kernel (kSchedBytes), then its trace
   float *resized;           // [batch][P] materialised resized map (resized depth only), else nullptr
   uint32_t cand_cap, emit_tiles;
   int32_t force_fallback;
+  int32_t hints;            // kHint* bits: L2 eviction priorities of the sub-batch pipeline (0 = none)
 };
+
+// L2 eviction-priority hints (d2pc_path.cu): keep what the emit will read again, let everything that is
+// touched once leave first
+constexpr int kHintScanKeep = 1;       // scan: depth loads evict-last (the emit reads the map again)
+constexpr int kHintEmitDepthFirst = 2; // emit: depth loads evict-first (last use) -- native depth only
+constexpr int kHintStreamFirst = 4;    // emit: colour loads and row stores evict-first
+constexpr int kHintResizedKeep = 8;    // scan: stores of the materialised resized map evict-last
+constexpr int kHintPipeline = 15;
 
 inline KParams make_kparams(const D2pcConfig &c, const float *d_depth, void *ws) {
   KParams k;
@@ -153,10 +196,13 @@ inline KParams make_kparams(const D2pcConfig &c, const float *d_depth, void *ws)
   k.fb_hist = (uint32_t *)(base + L.fbhist_off);
   k.xtab = (const TapEntry *)(base + L.tap_off);
   k.ytab = k.xtab + c.img_w;
+  k.sched = (uint32_t *)(base + L.sched_off);
+  k.sel = (SelShared *)(base + L.sel_off);
   k.resized = k.g.native ? nullptr : (float *)(base + L.resized_off);
   k.cand_cap = L.cand_cap;
   k.emit_tiles = L.emit_tiles;
   k.force_fallback = c.force_fallback;
+  k.hints = 0;
   return k;
 }
 
@@ -174,7 +220,48 @@ inline KParams per_pixel_view(const KParams &kp) {
   return v;
 }
 
+// frames [b0, b0 + nb) of a call's parameter block.  ring_slot >= 0: the slice's materialised resized maps
+// live at frames [ring_slot, ring_slot + nb) of the resized area (sub-batch pipeline: the area is reused as a
+// small ring so the maps stay in L2 between the scan that writes them and the emit that reads them).
+inline KParams slice_kparams(const KParams &kp, int b0, int nb, int ring_slot) {
+  KParams s = kp;
+  s.batch = nb;
+  s.depth = kp.depth + (size_t)b0 * kp.g.D;
+  s.state = kp.state + b0;
+  s.cand = kp.cand + (size_t)b0 * 2 * kp.cand_cap;
+  s.tile_state = kp.tile_state + (size_t)b0 * kp.emit_tiles;
+  s.fb_hist = kp.fb_hist + (size_t)b0 * kFbTargets * 256;
+  s.sel = kp.sel + b0;
+  if (kp.resized) s.resized = kp.resized + (size_t)(ring_slot >= 0 ? ring_slot : b0) * kp.g.P;
+  return s;
+}
+
+struct EmitArgs {
+  const uint8_t *bgr;
+  float *xyz, *rgb;
+  uint32_t *count;
+  PixelConsts pc;
+  int32_t use_z, drop_nf, want_bounds;
+  float z_min, z_max;
+};
+
 int validate_config(const D2pcConfig *cfg);   // d2pc_api.cu
+// d2pc_stats.cu
+int check_workspace(const D2pcConfig *cfg, const void *ws, size_t ws_bytes);
+int stats_prepare();
+int taps_launch(const KParams &kp, cudaStream_t st);
+constexpr int kStatsSample = 1, kStatsScanSelect = 2;
+int stats_launch(KParams kp, cudaStream_t st, int phases);
+int status_launch(const KParams &kp, int32_t *d_status, int32_t *d_any, cudaStream_t st);
+// d2pc_emit.cu
+EmitArgs make_emit_args(const D2pcConfig &cfg, const uint8_t *d_bgr, float *d_xyz, float *d_rgb, uint32_t *d_count);
+EmitArgs slice_emit_args(const EmitArgs &ea, const Geom &g, int b0);
+int emit_init_launch(const KParams &kp, cudaStream_t st);
+int bounds_export_launch(const KParams &kp, float *d_bounds, cudaStream_t st);
+int emit_validate(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr, void *d_workspace,
+                  size_t workspace_bytes, float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds);
+int emit_launch(const D2pcConfig &cfg, const KParams &kp, const EmitArgs &ea, float *d_bounds, cudaStream_t st,
+                int32_t smooth_k, const double *h_kernel, void *d_scratch);
 int record_cuda_error(cudaError_t e);          // d2pc_api.cu: returns D2PC_ERR_CUDA, stores text
 
 #define D2PC_CHECK_LAUNCH()                                  \
@@ -192,6 +279,34 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
+}
+// loads / stores carrying an explicit L2 eviction policy (createpolicy descriptor)
+__device__ __forceinline__ uint64_t l2_policy(bool first, bool last) {
+  uint64_t pf, pl, pn;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+  asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+  return first ? pf : (last ? pl : pn);
+}
+__device__ __forceinline__ float4 ldg_f4_pol(const float *p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_u32_pol(const void *p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void stg_f4_pol(float *p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+// shared -> global bulk copy (TMA unit) with an L2 policy; caller commits / waits the bulk group
+__device__ __forceinline__ void bulk_store_pol(void *gdst, uint32_t smem_addr, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(smem_addr), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
   uint32_t r;
@@ -344,6 +459,93 @@ __device__ __forceinline__ bool block_hist_select(ForEach for_each, uint32_t lo0
     __syncthreads();
   }
   return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-pass exact selection (the common case of block_hist_select at a fraction of its instruction
+// count): one bucket histogram over [lo0, lo0 + span] (kFastBins buckets of 2^shift keys), a block
+// scan that locates each wanted rank's bucket, one more visit of the keys that collects the
+// members of those buckets into short shared lists, and a rank pick inside the list.  The pieces
+// are separate so that a caller can fold its own per-key work into the first visit.
+// ------------------------------------------------------------------------------------------
+constexpr int kFastBinsLog = 12;
+constexpr uint32_t kFastBins = 1u << kFastBinsLog;
+constexpr uint32_t kFastListCap = 1024;   // members kept per wanted bucket
+
+__device__ __forceinline__ int fast_shift(uint32_t span) {
+  const int bits = span ? 32 - __clz(span) : 0;
+  return bits > kFastBinsLog ? bits - kFastBinsLog : 0;
+}
+
+// Locate, for every wanted rank, its bucket in a kFastBins-bucket histogram and the number of keys
+// in the buckets before it.  All threads call (blockDim.x * PER == kFastBins, PER a multiple of 4);
+// every thread gets the results.  bin[t] = 0xFFFFFFFF: rank outside the population.
+//   s_warp: 33 words, s_res: 2 * T words
+template <int T, bool GLOBAL = false>
+__device__ __forceinline__ void block_locate(const uint32_t *s_hist, const uint32_t (&rank)[T], const bool (&want)[T],
+                                             uint32_t (&bin)[T], uint32_t (&base)[T], uint32_t *s_warp,
+                                             uint32_t *s_res) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int per = (int)(kFastBins / blockDim.x);  // 4 for 1024 threads
+  if (tid < 2 * T) s_res[tid] = 0xFFFFFFFFu;
+  const uint32_t b0 = (uint32_t)tid * (uint32_t)per;
+  uint32_t sum = 0;
+  for (int i = 0; i < per; i += 4) {
+    const uint4 c = GLOBAL ? __ldcg(reinterpret_cast<const uint4 *>(s_hist + b0 + i))
+                           : *reinterpret_cast<const uint4 *>(s_hist + b0 + i);
+    sum += c.x + c.y + c.z + c.w;
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t x = lane < nwarp ? s_warp[lane] : 0u;
+    uint32_t in2 = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, in2, d);
+      if (lane >= d) in2 += y;
+    }
+    __syncwarp();
+    s_warp[lane] = in2 - x;  // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  uint32_t pref = s_warp[warp] + incl - sum;
+  bool mine = false;
+#pragma unroll
+  for (int t = 0; t < T; ++t) mine = mine || (want[t] && sum && pref <= rank[t] && rank[t] < pref + sum);
+  if (mine) {
+    for (int i = 0; i < per; ++i) {
+      const uint32_t c = GLOBAL ? __ldcg(s_hist + b0 + i) : s_hist[b0 + i];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (want[t] && c && pref <= rank[t] && rank[t] < pref + c) { s_res[2 * t] = b0 + i; s_res[2 * t + 1] = pref; }
+      pref += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < T; ++t) { bin[t] = s_res[2 * t]; base[t] = s_res[2 * t + 1]; }
+}
+
+// r-th smallest (0-based) of the n keys in a shared list; all threads call, result
+// broadcast through *s_out (caller synchronises before reading).
+__device__ __forceinline__ void block_pick(const uint32_t *list, uint32_t n, uint32_t r, uint32_t *s_out) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t k = list[i];
+    uint32_t smaller = 0, equal = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+      const uint32_t x = list[j];
+      smaller += x < k ? 1u : 0u;
+      equal += x == k ? 1u : 0u;
+    }
+    if (smaller <= r && r < smaller + equal) *s_out = k;
+  }
 }
 
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32

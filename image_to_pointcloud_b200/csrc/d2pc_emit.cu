@@ -14,153 +14,10 @@
 //     points[::stride], app.py:498-500, depends on it).
 #include <stdlib.h>
 
-#include "d2pc_device.cuh"
+#include "d2pc_emit_dev.cuh"
 
 namespace d2pc {
 
-struct EmitArgs {
-  const uint8_t *bgr;
-  float *xyz, *rgb;
-  uint32_t *count;
-  PixelConsts pc;
-  int32_t use_z, drop_nf, want_bounds;
-  float z_min, z_max;
-};
-
-__device__ __forceinline__ void stage_f4(float *s, float a, float b, float c, float d) {
-  *reinterpret_cast<float4 *>(s) = make_float4(a, b, c, d);
-}
-
-// per-CTA reduction of kept-point bounds -> 6 global atomics on ordered keys
-__device__ __forceinline__ void reduce_bounds(FrameState *fs, uint32_t mn[3], uint32_t mx[3],
-                                              uint32_t (*s_b)[kEmitThreads / 32]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    uint32_t a = warp_min(mn[c]), b = warp_max(mx[c]);
-    if (lane == 0) { s_b[c][warp] = a; s_b[3 + c][warp] = b; }
-  }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    const int c = threadIdx.x;
-    uint32_t r = s_b[c][0];
-    for (int w = 1; w < kEmitThreads / 32; ++w) r = c < 3 ? min(r, s_b[c][w]) : max(r, s_b[c][w]);
-    if (c < 3) { if (r != 0xFFFFFFFFu) atomicMin(&fs->bounds_min[c], r); }
-    else       { if (r != 0u) atomicMax(&fs->bounds_max[c - 3], r); }
-  }
-}
-
-// Copy n_f floats from shared staging (whose word 0 corresponds to global float index
-// g0 - s_off, i.e. staging is offset so that src and dst share 16 B alignment) to global.
-// The 16-byte aligned middle goes out as one TMA bulk copy issued by thread 0; the (at most three)
-// floats before and after it are stored by single threads.  The caller has executed
-// fence.proxy.async.shared::cta and a __syncthreads() after the last staging write.
-__device__ __forceinline__ void copy_out(const float *s, uint32_t s_off, uint32_t n_f, float *gbase,
-                                         size_t g0) {
-  float *galigned = gbase + (g0 - s_off);
-  const uint32_t span = s_off + n_f;
-  const uint32_t w_first = s_off ? 4u : 0u;      // first float of the aligned middle
-  const uint32_t w_last = span & ~3u;            // one past its last float
-  const uint32_t tid = threadIdx.x;
-  if (w_last > w_first) {
-    if (tid == 0) {
-      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s + w_first);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                   :: "l"(galigned + w_first), "r"(sa), "r"((w_last - w_first) * 4u) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    if (tid >= 32 && tid < 36) {        // head: floats [s_off, min(w_first, span))
-      const uint32_t w = s_off + (tid - 32);
-      if (w < w_first && w < span) stg_stream_f1(galigned + w, s[w]);
-    } else if (tid >= 64 && tid < 68) { // tail: floats [w_last, span)
-      const uint32_t w = w_last + (tid - 64);
-      if (w < span) stg_stream_f1(galigned + w, s[w]);
-    }
-  } else {  // fewer than one aligned chunk: a handful of floats
-    if (tid < 8) {
-      const uint32_t w = s_off + tid;
-      if (w < span) stg_stream_f1(galigned + w, s[w]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// fast path: step 1, native depth, 3-channel image, W % 4 == 0, no mask
-// ------------------------------------------------------------------------------------------
-// u8 -> f32 without the conversion pipe: byte k of w into the mantissa of 2^23, minus 2^23.
-__device__ __forceinline__ float byte_to_float(uint32_t w, uint32_t selector) {
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, selector)) - 8388608.0f;
-}
-#define D2PC_B0 0x7440u
-#define D2PC_B1 0x7441u
-#define D2PC_B2 0x7442u
-#define D2PC_B3 0x7443u
-
-// tile_state word: (flag << 32) | value ; flag 0 = not ready, 1 = tile aggregate, 2 = inclusive
-__device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long long *ts, int tile) {
-  const int lane = threadIdx.x & 31;
-  uint32_t exclusive = 0;
-  int base_idx = tile - 1;
-  while (true) {
-    const int idx = base_idx - lane;
-    unsigned long long st = (idx >= 0) ? ts[idx] : ((2ull << 32) | 0ull);
-    const uint32_t flag = (uint32_t)(st >> 32);
-    const unsigned inval = __ballot_sync(0xffffffffu, flag == 0u);
-    const unsigned incl = __ballot_sync(0xffffffffu, flag == 2u);
-    const int first_incl = incl ? (__ffs(incl) - 1) : 32;
-    const unsigned need = first_incl >= 31 ? 0xffffffffu : ((2u << first_incl) - 1u);
-    if (inval & need) continue;  // a needed predecessor has not published yet: re-read
-    uint32_t val = (lane <= first_incl) ? (uint32_t)st : 0u;
-    exclusive += warp_sum(val);
-    if (first_incl < 32) break;
-    base_idx -= 32;
-  }
-  return exclusive;
-}
-
-// ax-1 predicate.  Frames whose z is provably monotone in the raw depth (mask_mode 1) compare the
-// raw value against the frame's depth-space interval; all other frames compare the emitted z.
-struct MaskParams {
-  int32_t mode;
-  float lo, hi;
-};
-__device__ __forceinline__ MaskParams load_mask(const FrameState *fs) {
-  MaskParams m;
-  m.mode = fs->mask_mode; m.lo = fs->mask_lo; m.hi = fs->mask_hi;
-  return m;
-}
-__device__ __forceinline__ bool mask_keep(float raw, float z32, const MaskParams &m, const EmitArgs &ea) {
-  bool kk = true;
-  if (ea.use_z) {
-    if (m.mode == 1) kk = (raw >= m.lo) && (raw <= m.hi);
-    else kk = (z32 >= ea.z_min) && (z32 <= ea.z_max);
-  }
-  if (ea.drop_nf && !is_finite_f32(raw)) kk = false;
-  return kk;
-}
-
-// mask_interval (d2pc_math.h) by one warp: 32 probes of the ordered key space per round instead of
-// one, so the two searches take ~7 rounds each.  The predicate is monotone (false -> true).
-template <typename Pred>
-__device__ __forceinline__ uint32_t warp_first_true(uint32_t lo, uint32_t hi, Pred pred) {
-  // invariant: pred is false for keys < lo and true for hi
-  const int lane = threadIdx.x & 31;
-  while (lo < hi) {
-    const unsigned long long span = (unsigned long long)(hi - lo);
-    const uint32_t k = lo + (uint32_t)((span * (unsigned long long)(lane + 1)) / 33ull);  // < hi
-    const bool p = pred(k);
-    const unsigned m = __ballot_sync(0xffffffffu, p);
-    if (m == 0u) {
-      lo = __shfl_sync(0xffffffffu, k, 31) + 1u;
-    } else {
-      const int j = __ffs(m) - 1;
-      hi = __shfl_sync(0xffffffffu, k, j);
-      if (j > 0) lo = __shfl_sync(0xffffffffu, k, j - 1) + 1u;
-    }
-  }
-  return lo;
-}
 
 __global__ void __launch_bounds__(32) mask_prepare_kernel(KParams kp, EmitArgs ea, int pc_simple) {
   FrameState *fs = kp.state + blockIdx.x;
@@ -278,185 +135,9 @@ __global__ void __launch_bounds__(1024) mask_offsets_kernel(KParams kp, uint32_t
   if (tid == 0) count[b] = s_carry;
 }
 
-// One tile of 1024 consecutive output rows per CTA, 4 consecutive rows per thread (they share an
-// image row).  STEP 1: one 16 B depth load + 12 colour bytes; STEP 2 / 4 (density medium / low):
-// the same tiling over the strided output grid, loading only the sectors that hold sampled
-// pixels.  The depth map is always per-pixel here (the scan materialises a resized map).  MASK: depth-range / non-finite mask with ordered
-// compaction (CTA scan + decoupled look-back over the frame's tiles, tiles dispatched in order).
-// High occupancy matters more than per-thread ILP here (measured: 6 CTAs/SM beat 3-5 and beat a
-// persistent register-prefetching variant), hence MIN_BLOCKS.
-struct FastArgs {
-  uint32_t tiles_per_frame, total_tiles, batch;
-  unsigned long long magic_w;  // ceil(2^40 / W): p / W == (p * magic_w) >> 40 for p * W < 2^40
-  int32_t pc_simple;
-};
-
-template <int STEP, bool MASK, bool BOUNDS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(kEmitThreads, MIN_BLOCKS) emit_fast_kernel(KParams kp, EmitArgs ea, FastArgs fa) {
-  static_assert(STEP == 1 || !MASK, "the masked fast path is stride 1 only");
-  extern __shared__ __align__(16) float s_stage[];  // xyz [3072 + 4] | rgb [3072 + 4]
-  __shared__ uint32_t s_warp[kEmitThreads / 32];
-  __shared__ uint32_t s_b[6][kEmitThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // P = rows of the output grid (nu x nv); for STEP 1 the grid is the image itself
-  const uint32_t P = kp.g.N, W = (uint32_t)kp.g.W, NU = (uint32_t)kp.g.nu;
-  const uint32_t t = blockIdx.x;
-  const uint32_t b = t / fa.tiles_per_frame, tile = t - b * fa.tiles_per_frame;
-  FrameState *fs = kp.state + b;
-  if (fs->status != D2PC_FRAME_READY) return;  // uniform per CTA (and per frame: no tile of it publishes)
-  const uint32_t tile_base = tile * (uint32_t)kEmitTile;
-  const uint32_t p0 = tile_base + 4u * (uint32_t)tid;   // first of this thread's 4 output rows
-  float *s_xyz = s_stage;
-  float *s_rgb = s_stage + (kEmitTile * 3 + 4);
-  float o[12];
-  uint32_t c0 = 0, c1 = 0, c2 = 0;
-  bool keep[4] = {false, false, false, false};
-  uint32_t my_cnt = 0;
-  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
-  if (p0 < P) {
-    // (jv, ju) in the output grid; magic_w divides by nu (== W for STEP 1)
-    const uint32_t jv = (uint32_t)(((unsigned long long)p0 * fa.magic_w) >> 40), ju = p0 - jv * NU;
-    const uint32_t v = jv * (uint32_t)STEP, u = ju * (uint32_t)STEP;
-    const size_t pix = (size_t)b * kp.g.P + (size_t)v * W + u;  // first source pixel (same row for all 4)
-    float raw[4];
-    const uint8_t *cp = ea.bgr + pix * 3;
-    if (STEP == 1) {
-      const float4 d4 = ldg_stream_f4(kp.depth + pix);
-      raw[0] = d4.x; raw[1] = d4.y; raw[2] = d4.z; raw[3] = d4.w;
-      c0 = ldg_stream_u32(cp); c1 = ldg_stream_u32(cp + 4); c2 = ldg_stream_u32(cp + 8);
-    } else if (STEP == 2) {
-      // pixels u, u+2, u+4, u+6: two 16 B depth loads, the 24 colour bytes of 8 pixels
-      const float4 da = ldg_stream_f4(kp.depth + pix), db = ldg_stream_f4(kp.depth + pix + 4);
-      raw[0] = da.x; raw[1] = da.z; raw[2] = db.x; raw[3] = db.z;
-      const uint32_t w0 = ldg_stream_u32(cp), w1 = ldg_stream_u32(cp + 4), w2 = ldg_stream_u32(cp + 8);
-      const uint32_t w3 = ldg_stream_u32(cp + 12), w4 = ldg_stream_u32(cp + 16), w5 = ldg_stream_u32(cp + 20);
-      // repack as the STEP 1 layout: c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
-      const uint32_t px1 = __byte_perm(w1, w2, 0x0432);  // bytes 6,7,8   -> B1 G1 R1 .
-      const uint32_t px3 = __byte_perm(w4, w5, 0x0432);  // bytes 18,19,20 -> B3 G3 R3 .
-      c0 = __byte_perm(w0, px1, 0x4210);                 // B0 G0 R0 B1
-      c1 = __byte_perm(px1, w3, 0x5421);                 // G1 R1 B2 G2
-      c2 = __byte_perm(w3, px3, 0x6542);                 // R2 B3 G3 R3
-    } else {
-      // pixels u, u+4, u+8, u+12: one 4 B load each (12-byte colour pitch keeps u32 loads aligned)
-      raw[0] = __ldg(kp.depth + pix); raw[1] = __ldg(kp.depth + pix + 4);
-      raw[2] = __ldg(kp.depth + pix + 8); raw[3] = __ldg(kp.depth + pix + 12);
-      const uint32_t q0 = ldg_stream_u32(cp), q1 = ldg_stream_u32(cp + 12), q2 = ldg_stream_u32(cp + 24),
-                     q3 = ldg_stream_u32(cp + 36);
-      c0 = __byte_perm(q0, q1, 0x4210);   // B0 G0 R0 B1
-      c1 = __byte_perm(q1, q2, 0x5421);   // G1 R1 B2 G2
-      c2 = __byte_perm(q2, q3, 0x6542);   // R2 B3 G3 R3
-    }
-    if (!MASK) {
-      // colours first: once staged, their registers are free for the float64 chain below
-      float *sr = s_rgb + 12 * tid;
-      // bytes (little endian): c0 = B0 G0 R0 B1, c1 = G1 R1 B2 G2, c2 = R2 B3 G3 R3
-      stage_f4(sr, byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
-               byte_to_float(c1, D2PC_B1));
-      stage_f4(sr + 4, byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3), byte_to_float(c2, D2PC_B0),
-               byte_to_float(c1, D2PC_B3));
-      stage_f4(sr + 8, byte_to_float(c1, D2PC_B2), byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2),
-               byte_to_float(c2, D2PC_B1));
-    }
-    const NormParams np_ = fs->norm;
-    const MaskParams mp = load_mask(fs);
-    if (np_.simple && fa.pc_simple) {  // uniform per frame
-      const double ux0 = (double)(int32_t)u - ea.pc.cx;
-      const double vy = (double)(int32_t)v - ea.pc.cy;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        simple_point(raw[k], ux0 + (double)(k * STEP), vy, np_, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double n = normalised_depth(raw[k], np_, ea.pc.invert);
-        back_project(n, (int32_t)u + k * STEP, (int32_t)v, ea.pc, &o[3 * k], &o[3 * k + 1], &o[3 * k + 2]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      bool kk = true;
-      if (MASK) kk = mask_keep(raw[k], o[3 * k + 2], mp, ea);  // same predicate as mask_count_kernel
-      keep[k] = kk;
-      my_cnt += kk ? 1u : 0u;
-      if (BOUNDS && kk) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          uint32_t key = float_to_key(o[3 * k + c]);
-          mn[c] = min(mn[c], key); mx[c] = max(mx[c], key);
-        }
-      }
-    }
-  }
-  if (!MASK) {
-    if (p0 < P) {
-      float *sx = s_xyz + 12 * tid;
-      stage_f4(sx, o[0], o[1], o[2], o[3]);
-      stage_f4(sx + 4, o[4], o[5], o[6], o[7]);
-      stage_f4(sx + 8, o[8], o[9], o[10], o[11]);
-    }
-    // The tile's rows are contiguous in both outputs (rows * 12 bytes each, a multiple of 16 at 16-byte
-    // aligned addresses): one elected thread hands each staged array to the TMA unit as a bulk
-    // shared -> global copy, the other threads are done.
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged rows visible to the async proxy
-    __syncthreads();
-    const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
-    const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
-    if (tid == 0) {
-      const uint32_t bytes = rows * 12u;  // rows % 4 == 0 here
-      const uint32_t sx = (uint32_t)__cvta_generic_to_shared(s_xyz), sr = (uint32_t)__cvta_generic_to_shared(s_rgb);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(ea.xyz + g0), "r"(sx), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(ea.rgb + g0), "r"(sr), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging may be released once it has been read
-      if (tile == 0) ea.count[b] = kp.g.N;
-    }
-  } else {
-    // CTA exclusive scan of the per-thread keep counts
-    uint32_t incl = my_cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += y;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kEmitThreads / 32; ++w) {
-      uint32_t c = s_warp[w];
-      if (w < warp) warp_off += c;
-      total += c;
-    }
-    uint32_t local = warp_off + incl - my_cnt;
-    // destination row: exclusive prefix of the kept counts, computed before this launch by
-    // mask_count_kernel + mask_offsets_kernel (no inter-CTA dependency inside emit)
-    const uint32_t dest_row = (uint32_t)(kp.tile_state[(size_t)b * kp.emit_tiles + tile] >> 32);
-    const size_t g0 = ((size_t)b * kp.g.N + dest_row) * 3;
-    const uint32_t s_off = (uint32_t)(g0 & 3);
-    const float col[12] = {
-        byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
-        byte_to_float(c1, D2PC_B1), byte_to_float(c1, D2PC_B0), byte_to_float(c0, D2PC_B3),
-        byte_to_float(c2, D2PC_B0), byte_to_float(c1, D2PC_B3), byte_to_float(c1, D2PC_B2),
-        byte_to_float(c2, D2PC_B3), byte_to_float(c2, D2PC_B2), byte_to_float(c2, D2PC_B1)};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!keep[k]) continue;
-      const uint32_t w = s_off + 3u * local;
-      s_xyz[w] = o[3 * k]; s_xyz[w + 1] = o[3 * k + 1]; s_xyz[w + 2] = o[3 * k + 2];
-      s_rgb[w] = col[3 * k]; s_rgb[w + 1] = col[3 * k + 1]; s_rgb[w + 2] = col[3 * k + 2];
-      local++;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0);
-    copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0);
-  }
-  if (BOUNDS) reduce_bounds(fs, mn, mx, s_b);
-}
-
 template <int STEP, bool MASK, int MIN_BLOCKS>
 static int launch_emit_fast(const KParams &kp, const EmitArgs &ea, const FastArgs &fa, cudaStream_t st) {
-  const size_t smem = 2 * ((size_t)kEmitTile * 3 + 4) * sizeof(float);
+  const size_t smem = kEmitStageBytes;
   if (ea.want_bounds) emit_fast_kernel<STEP, MASK, true, 5><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
   else emit_fast_kernel<STEP, MASK, false, MIN_BLOCKS><<<fa.total_tiles, kEmitThreads, smem, st>>>(kp, ea, fa);
   return D2PC_OK;
@@ -630,8 +311,9 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0);
-  copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0);
+  const uint64_t pol_o = l2_policy((kp.hints & kHintStreamFirst) != 0, false);
+  copy_out(s_xyz, s_off, total * 3u, ea.xyz, g0, pol_o);
+  copy_out(s_rgb, s_off, total * 3u, ea.rgb, g0, pol_o);
   if (ea.want_bounds) reduce_bounds(fs, mn, mx, s_b);
 }
 
@@ -663,82 +345,85 @@ __global__ void bounds_export_kernel(KParams kp, float *d_bounds) {
 
 using namespace d2pc;
 
-static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr, void *d_workspace,
-                     size_t workspace_bytes, float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds,
-                     void *stream, int32_t smooth_k, const double *h_kernel, void *d_scratch, size_t scratch_bytes) {
-  int rc = validate_config(cfg);
-  if (rc) return rc;
-  const bool smooth = smooth_k > 0;
-  if (smooth) {
-    if ((smooth_k & 1) == 0 || smooth_k < 3 || smooth_k > D2PC_MAX_SMOOTH_KSIZE) return D2PC_ERR_UNSUPPORTED;
-    if (!h_kernel || !d_scratch) return D2PC_ERR_INVALID_ARGUMENT;
-    const size_t need = 2 * (size_t)cfg->batch * (size_t)cfg->img_h * (size_t)cfg->img_w * sizeof(double);
-    if (scratch_bytes < need) return D2PC_ERR_WORKSPACE_TOO_SMALL;
-    if (((uintptr_t)d_scratch & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
-  }
-  if (!d_workspace || !d_depth || !d_xyz || !d_rgb || !d_count) return D2PC_ERR_INVALID_ARGUMENT;
-  if (cfg->img_c >= 3 && !d_bgr) return D2PC_ERR_INVALID_ARGUMENT;
-  if (cfg->want_bounds && !d_bounds) return D2PC_ERR_INVALID_ARGUMENT;
-  if (workspace_bytes < make_layout(*cfg).total) return D2PC_ERR_WORKSPACE_TOO_SMALL;
-  if ((((uintptr_t)d_xyz | (uintptr_t)d_rgb) & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
-  cudaStream_t st = (cudaStream_t)stream;
-  // emit always reads a per-pixel map: the input, or the resized map the scan materialised
-  KParams kp = per_pixel_view(make_kparams(*cfg, d_depth, d_workspace));
+namespace d2pc {
+
+EmitArgs make_emit_args(const D2pcConfig &cfg, const uint8_t *d_bgr, float *d_xyz, float *d_rgb, uint32_t *d_count) {
   EmitArgs ea;
   ea.bgr = d_bgr; ea.xyz = d_xyz; ea.rgb = d_rgb; ea.count = d_count;
-  ea.pc.scale = cfg->depth_scale; ea.pc.cx = cfg->cx; ea.pc.cy = cfg->cy; ea.pc.f = cfg->f;
-  ea.pc.inv_f = 1.0 / cfg->f; ea.pc.invert = cfg->invert;
-  ea.use_z = cfg->use_z_range; ea.drop_nf = cfg->drop_nonfinite; ea.want_bounds = cfg->want_bounds;
-  ea.z_min = cfg->z_min; ea.z_max = cfg->z_max;
-  const bool mask = cfg->use_z_range || cfg->drop_nonfinite;
-  dim3 grid(kp.emit_tiles, cfg->batch);
+  ea.pc.scale = cfg.depth_scale; ea.pc.cx = cfg.cx; ea.pc.cy = cfg.cy; ea.pc.f = cfg.f;
+  ea.pc.inv_f = 1.0 / cfg.f; ea.pc.invert = cfg.invert;
+  ea.use_z = cfg.use_z_range; ea.drop_nf = cfg.drop_nonfinite; ea.want_bounds = cfg.want_bounds;
+  ea.z_min = cfg.z_min; ea.z_max = cfg.z_max;
+  return ea;
+}
+
+// frames [b0, b0 + nb) of the output side of a call (the parameter block is sliced by slice_kparams)
+EmitArgs slice_emit_args(const EmitArgs &ea, const Geom &g, int b0) {
+  EmitArgs s = ea;
+  if (ea.bgr) s.bgr = ea.bgr + (size_t)b0 * g.P * (size_t)g.C;
+  s.xyz = ea.xyz + (size_t)b0 * g.N * 3;
+  s.rgb = ea.rgb + (size_t)b0 * g.N * 3;
+  s.count = ea.count + b0;
+  return s;
+}
+
+// Emission of the kp.batch frames of a (sliced) parameter block; kp is the block as make_kparams /
+// slice_kparams produced it (the per-pixel view is applied here).
+int emit_launch(const D2pcConfig &cfg, const KParams &kp_in, const EmitArgs &ea, float *d_bounds, cudaStream_t st,
+                int32_t smooth_k, const double *h_kernel, void *d_scratch) {
+  const bool smooth = smooth_k > 0;
+  // emit always reads a per-pixel map: the input, or the resized map the scan materialised
+  const KParams kp = per_pixel_view(kp_in);
+  const int nb = kp.batch;
+  const bool mask = cfg.use_z_range || cfg.drop_nonfinite;
+  dim3 grid(kp.emit_tiles, nb);
   SmoothArgs sa;
   sa.rows = nullptr;
   sa.ksize = 0;
   if (smooth) {
-    double *n64 = (double *)d_scratch, *rows = n64 + (size_t)cfg->batch * kp.g.P;
+    double *n64 = (double *)d_scratch, *rows = n64 + (size_t)nb * kp.g.P;
     sa.rows = rows;
     sa.ksize = smooth_k;
     for (int i = 0; i < smooth_k; ++i) sa.k[i] = h_kernel[i];
-    dim3 sg(148 * 4, cfg->batch);
-    smooth_norm_kernel<<<sg, 256, 0, st>>>(kp, cfg->invert, n64);
+    dim3 sg(148 * 4, nb);
+    smooth_norm_kernel<<<sg, 256, 0, st>>>(kp, cfg.invert, n64);
     D2PC_CHECK_LAUNCH();
     smooth_rows_kernel<<<sg, 256, 0, st>>>(kp, sa, n64, rows);
     D2PC_CHECK_LAUNCH();
   }
   // fast path: 3-channel image, 4 consecutive output rows per thread in one image row, vector loads.
   // stride 1: W % 4 == 0; stride 2: W % 8 == 0; stride 4: W % 16 == 0 (unmasked only for strides > 1)
-  const bool fast = !smooth && cfg->img_c == 3 && (cfg->img_w % (4 * cfg->step)) == 0 && (cfg->step == 1 || !mask) &&
-                    (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)d_bgr & 3u) == 0u) && (kp.g.N & 3u) == 0u &&
+  const bool fast = !smooth && cfg.img_c == 3 && (cfg.img_w % (4 * cfg.step)) == 0 && (cfg.step == 1 || !mask) &&
+                    (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)ea.bgr & 3u) == 0u) && (kp.g.N & 3u) == 0u &&
                     ((unsigned long long)kp.g.N * (unsigned long long)kp.g.nu < (1ull << 40));
-  if (mask || cfg->want_bounds) {
-    emit_init_kernel<<<cfg->batch, 256, 0, st>>>(kp, (mask && !fast) ? 1 : 0);
+  if (mask || cfg.want_bounds) {
+    emit_init_kernel<<<nb, 256, 0, st>>>(kp, (mask && !fast) ? 1 : 0);
     D2PC_CHECK_LAUNCH();
   }
   if (mask) {
     // a smoothed z is not a function of the pixel's own depth: exact z compare (mode 0) in that case
-    mask_prepare_kernel<<<cfg->batch, 32, 0, st>>>(kp, ea, (!smooth && consts_simple(ea.pc)) ? 1 : 0);
+    mask_prepare_kernel<<<nb, 32, 0, st>>>(kp, ea, (!smooth && consts_simple(ea.pc)) ? 1 : 0);
     D2PC_CHECK_LAUNCH();
   }
   if (fast) {
     if (mask) {
-      const uint32_t total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
+      const uint32_t total_tiles = kp.emit_tiles * (uint32_t)nb;
       mask_count_kernel<<<(total_tiles + kCountWarps - 1) / kCountWarps, kCountWarps * 32, 0, st>>>(kp, ea, kp.emit_tiles,
                                                                                                    total_tiles);
       D2PC_CHECK_LAUNCH();
-      mask_offsets_kernel<<<cfg->batch, 1024, 0, st>>>(kp, d_count);
+      mask_offsets_kernel<<<nb, 1024, 0, st>>>(kp, ea.count);
       D2PC_CHECK_LAUNCH();
     }
     FastArgs fa;
     fa.tiles_per_frame = kp.emit_tiles;
-    fa.total_tiles = kp.emit_tiles * (uint32_t)cfg->batch;
-    fa.batch = (uint32_t)cfg->batch;
+    fa.total_tiles = kp.emit_tiles * (uint32_t)nb;
+    fa.batch = (uint32_t)nb;
     fa.magic_w = ((1ull << 40) + (unsigned long long)kp.g.nu - 1ull) / (unsigned long long)kp.g.nu;
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
     int rcl;
     if (mask) rcl = launch_emit_fast<1, true, 5>(kp, ea, fa, st);
-    else if (cfg->step == 1) rcl = launch_emit_fast<1, false, 6>(kp, ea, fa, st);
-    else if (cfg->step == 2) rcl = launch_emit_fast<2, false, 6>(kp, ea, fa, st);
+    else if (cfg.step == 1) rcl = launch_emit_fast<1, false, 6>(kp, ea, fa, st);
+    else if (cfg.step == 2) rcl = launch_emit_fast<2, false, 6>(kp, ea, fa, st);
     else rcl = launch_emit_fast<4, false, 6>(kp, ea, fa, st);
     if (rcl) return rcl;
   } else if (smooth) {
@@ -749,11 +434,54 @@ static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t 
     else emit_generic_kernel<true, false, false><<<grid, kEmitThreads, 0, st>>>(kp, ea, sa);
   }
   D2PC_CHECK_LAUNCH();
-  if (cfg->want_bounds) {
-    bounds_export_kernel<<<(cfg->batch * 6 + 127) / 128, 128, 0, st>>>(kp, d_bounds);
+  if (cfg.want_bounds) {
+    bounds_export_kernel<<<(nb * 6 + 127) / 128, 128, 0, st>>>(kp, d_bounds);
     D2PC_CHECK_LAUNCH();
   }
   return D2PC_OK;
+}
+
+int emit_init_launch(const KParams &kp, cudaStream_t st) {
+  emit_init_kernel<<<kp.batch, 256, 0, st>>>(kp, 0);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
+int bounds_export_launch(const KParams &kp, float *d_bounds, cudaStream_t st) {
+  bounds_export_kernel<<<(kp.batch * 6 + 127) / 128, 128, 0, st>>>(kp, d_bounds);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
+int emit_validate(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr, void *d_workspace,
+                  size_t workspace_bytes, float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds) {
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  if (!d_workspace || !d_depth || !d_xyz || !d_rgb || !d_count) return D2PC_ERR_INVALID_ARGUMENT;
+  if (cfg->img_c >= 3 && !d_bgr) return D2PC_ERR_INVALID_ARGUMENT;
+  if (cfg->want_bounds && !d_bounds) return D2PC_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < make_layout(*cfg).total) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)d_xyz | (uintptr_t)d_rgb) & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
+  return D2PC_OK;
+}
+
+}  // namespace d2pc
+
+static int emit_impl(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr, void *d_workspace,
+                     size_t workspace_bytes, float *d_xyz, float *d_rgb, uint32_t *d_count, float *d_bounds,
+                     void *stream, int32_t smooth_k, const double *h_kernel, void *d_scratch, size_t scratch_bytes) {
+  int rc = emit_validate(cfg, d_depth, d_bgr, d_workspace, workspace_bytes, d_xyz, d_rgb, d_count, d_bounds);
+  if (rc) return rc;
+  if (smooth_k > 0) {
+    if ((smooth_k & 1) == 0 || smooth_k < 3 || smooth_k > D2PC_MAX_SMOOTH_KSIZE) return D2PC_ERR_UNSUPPORTED;
+    if (!h_kernel || !d_scratch) return D2PC_ERR_INVALID_ARGUMENT;
+    const size_t need = 2 * (size_t)cfg->batch * (size_t)cfg->img_h * (size_t)cfg->img_w * sizeof(double);
+    if (scratch_bytes < need) return D2PC_ERR_WORKSPACE_TOO_SMALL;
+    if (((uintptr_t)d_scratch & 15u) != 0) return D2PC_ERR_INVALID_ARGUMENT;
+  }
+  const KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  const EmitArgs ea = make_emit_args(*cfg, d_bgr, d_xyz, d_rgb, d_count);
+  return emit_launch(*cfg, kp, ea, d_bounds, (cudaStream_t)stream, smooth_k, h_kernel, d_scratch);
 }
 
 // ------------------------------------------------------------------------------------------

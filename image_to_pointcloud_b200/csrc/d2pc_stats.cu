@@ -18,7 +18,7 @@
 // Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, queue
 // overflow, collapsed percentiles) are only marked; d2pc_stats_fallback_enqueue runs the
 // input-agnostic exact path (8-bit radix select, nanmedian repair) for those.
-#include "d2pc_device.cuh"
+#include "d2pc_stats_dev.cuh"
 
 namespace d2pc {
 
@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(KParams kp) {
 // sample_kernel
 // ------------------------------------------------------------------------------------------
 template <bool NATIVE>
-__global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
+__global__ void __launch_bounds__(kSelThreads, 1) sample_kernel(KParams kp) {
   extern __shared__ uint32_t s_hist[];  // 4 << kSelBits words
   __shared__ uint32_t s_bad, s_min, s_max;
   __shared__ uint32_t s_res[2 * 4 + 40];
+  __shared__ uint32_t s_warp[33], s_cnt[4], s_lmin[4], s_lmax[4], s_out[4];
   const int b = blockIdx.x;
   FrameState *fs = kp.state + b;
   const float *frame = kp.depth + (size_t)b * kp.g.D;
@@ -77,15 +78,26 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     for (int i = 0; i < 2; ++i) {
       fs->below[i] = 0; fs->eqL[i] = 0; fs->inside[i] = 0; fs->eqU[i] = 0;
     }
+    fs->above1 = 0;
     fs->n_nonfinite = 0; fs->n_nan = 0; fs->nqueue[0] = 0; fs->nqueue[1] = 0;
     fs->min_key = 0xFFFFFFFFu; fs->max_key = 0u;
     for (int i = 0; i < 4; ++i) fs->sel_key[i] = 0;
     fs->sel_fail = 0; fs->sel_done = 0;
+    if (b == 0)
+      for (int i = 0; i <= kSchedQueues; ++i) kp.sched[32 * i] = 0u;
+    {  // trace of the persistent path kernel: min-slots start at ~0, max-slots at 0
+      unsigned long long *tr = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(kp.sched) + kSchedBytes) + (size_t)b * 8;
+      for (int i = 0; i < 8; ++i) tr[i] = (i == 0 || i == 6) ? ~0ull : 0ull;
+    }
     fs->status = D2PC_FRAME_PENDING;
     fs->fb_active = 0; fs->fb_any_nan = 0;
     fs->norm.has_nonfinite = 0;
     fs->norm.median = 0.0f;
     fs->norm.simple = 0;
+  }
+  {  // scratch of the cooperative selection (persistent path kernel)
+    uint32_t *z = reinterpret_cast<uint32_t *>(kp.sel + b);
+    for (uint32_t i = tid; i < sizeof(SelShared) / 4; i += kSelThreads) z[i] = 0u;
   }
   if (n <= (uint32_t)kSortCap) {  // small frame: every finite key is a candidate
     if (tid == 0) {
@@ -136,10 +148,71 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
     rank[2 * br + 0] = open_lo[br] ? 0u : (uint32_t)iL;
     rank[2 * br + 1] = open_hi[br] ? S - 1 : (uint32_t)iU;
   }
-  block_hist_select<4, kSelBits>([&](auto f) {
+  // exact sample order statistics: two-pass selection (bucket histogram -> the wanted buckets' members)
+  {
+    uint32_t *s_list = s_hist + kFastBins;  // [4][kFastListCap]
+    const uint32_t lo0 = s_min, span = s_max - s_min;
+    const int shift = fast_shift(span);
+    for (uint32_t i = tid; i < kFastBins; i += kSelThreads) s_hist[i] = 0u;
+    if (tid < 4) { s_cnt[tid] = 0u; s_lmin[tid] = 0xFFFFFFFFu; s_lmax[tid] = 0u; s_out[tid] = 0u; }
+    __syncthreads();
 #pragma unroll
-    for (int e = 0; e < E; ++e) f(k[e]);
-  }, s_min, s_max, rank, out, s_hist, s_res);
+    for (int e = 0; e < E; ++e) atomicAdd(&s_hist[(k[e] - lo0) >> shift], 1u);
+    __syncthreads();
+    uint32_t bin[4], base[4];
+    const bool want[4] = {true, true, true, true};
+    block_locate<4>(s_hist, rank, want, bin, base, s_warp, s_res);
+    bool slow = false;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) slow = slow || bin[t] == 0xFFFFFFFFu;  // cannot happen (ranks < S)
+    if (!slow && shift == 0) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) out[t] = lo0 + bin[t];
+    } else if (!slow) {
+      int owner[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        owner[t] = t;
+#pragma unroll
+        for (int u = t - 1; u >= 0; --u)
+          if (bin[u] == bin[t]) owner[t] = u;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint32_t bk = (k[e] - lo0) >> shift;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (owner[t] == t && bk == bin[t]) {
+            const uint32_t idx = atomicAdd(&s_cnt[t], 1u);
+            if (idx < kFastListCap) s_list[t * kFastListCap + idx] = k[e];
+            atomicMin(&s_lmin[t], k[e]);
+            atomicMax(&s_lmax[t], k[e]);
+          }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (owner[t] == t && s_cnt[t] > kFastListCap && s_lmin[t] != s_lmax[t]) slow = true;
+      if (!slow) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int o = owner[t];
+          if (s_lmin[o] == s_lmax[o]) { if (tid == 0) s_out[t] = s_lmin[o]; }
+          else block_pick(s_list + o * kFastListCap, s_cnt[o], rank[t] - base[t], &s_out[t]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) out[t] = s_out[t];
+      }
+    }
+    if (slow) {  // uniform: heavy ties inside one bucket -> the general multi-level selection
+      __syncthreads();
+      block_hist_select<4, kSelBits>([&](auto f) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) f(k[e]);
+      }, s_min, s_max, rank, out, s_hist, s_res);
+    }
+  }
   if (tid < 2) {
     fs->brL[tid] = open_lo[tid] ? 0u : out[2 * tid + 0];
     fs->brU[tid] = open_hi[tid] ? 0xFFFFFFFFu : out[2 * tid + 1];
@@ -150,97 +223,21 @@ __global__ void __launch_bounds__(kSelThreads) sample_kernel(KParams kp) {
 // ------------------------------------------------------------------------------------------
 // scan_kernel
 // ------------------------------------------------------------------------------------------
-// One streaming pass, ~10 instructions per pixel on the common path: float compares against the
-// bracket bounds (as floats; -0.0 == +0.0 here and in the rare path, consistently), per-thread
-// "below" counters, and a rare path (about 4% of pixels: inside a bracket, or non-finite) that
-// appends the key to the CTA's staging list or bumps an equal-to-bound / non-finite counter.
-// min/max are not tracked: a frame whose percentiles collapse (p98 <= p2) goes to the exact
+// One streaming pass, 4 instructions per pixel on the common path.  With the brackets [L0, U0] (around the
+// 2% ranks) and [L1, U1] (around the 98% ranks), about 94% of the pixels lie strictly between U0 and L1 and
+// need nothing at all: they are below bracket 1 and above bracket 0, which the frame's totals account for.
+// Every other value (about 6%: below or inside bracket 0, inside or above bracket 1, or non-finite -- every
+// ordered compare with NaN is false) is appended to the thread's private queue column in shared memory and
+// classified in the epilogue: counted (below L0, above U1, non-finite) or forwarded to the bracket's raw
+// queue in global memory.  Compares are float compares (-0.0 == +0.0), here and in the selection,
+// consistently.  min/max are not tracked: a frame whose percentiles collapse (p98 <= p2) goes to the exact
 // fallback, which computes them.
 template <int QD>
 struct ScanSharedT {
   float pqueue[QD][kScanThreads];  // per-thread deferred values, slot-major
-  uint32_t qtotal[2], gbase[2];
-  uint32_t red[2][kScanThreads / 32];
+  ScanFlushSmem flush;
 };
 using ScanShared = ScanSharedT<kScanPerThread>;
-
-// Common path, 11 predicated instructions, no branch, no atomic: count "below" for both brackets
-// and, when the value is inside a bracket or non-finite (about 4% of pixels), store it in the
-// thread's private queue column in shared memory (qaddr = shared-space byte address of the next
-// free slot).  NaN: every ordered compare is false; setp.gtu (unordered greater) is true.
-__device__ __forceinline__ void scan_value(float v, const float Lf[2], const float Uf[2], uint32_t &b0,
-                                           uint32_t &b1, uint32_t &qaddr) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred lt0, lt1, in0, any;\n\t"
-      ".reg .f32 av;\n\t"
-      "setp.lt.f32 lt0, %3, %4;\n\t"
-      "setp.lt.f32 lt1, %3, %5;\n\t"
-      "@lt0 add.u32 %0, %0, 1;\n\t"
-      "@lt1 add.u32 %1, %1, 1;\n\t"
-      "setp.le.and.f32 in0, %3, %6, !lt0;\n\t"
-      "setp.le.and.f32 any, %3, %7, !lt1;\n\t"
-      "or.pred any, any, in0;\n\t"
-      "abs.f32 av, %3;\n\t"
-      "setp.gtu.or.f32 any, av, 0f7F7FFFFF, any;\n\t"
-      "@any st.shared.f32 [%2], %3;\n\t"
-      "@any add.u32 %2, %2, %8;\n\t"
-      "}"
-      : "+r"(b0), "+r"(b1), "+r"(qaddr)
-      : "f"(v), "f"(Lf[0]), "f"(Lf[1]), "f"(Uf[0]), "f"(Uf[1]), "n"(kScanThreads * 4)
-      : "memory");
-}
-
-__device__ __forceinline__ void bracket_floats(const FrameState *fs, float Lf[2], float Uf[2]) {
-#pragma unroll
-  for (int br = 0; br < 2; ++br) {
-    const uint32_t L = fs->brL[br], U = fs->brU[br];
-    Lf[br] = (L == 0u) ? -__int_as_float(0x7F800000) : key_to_float(L);           // open below
-    Uf[br] = (U == 0xFFFFFFFFu) ? __int_as_float(0x7F800000) : key_to_float(U);   // open above
-  }
-}
-
-// CTA totals -> 4 global atomics; deferred values -> the two brackets' raw queues
-// (queue 0: v <= U0 or non-finite; queue 1: v >= L1; a value inside both goes to both)
-template <int QD>
-__device__ __forceinline__ void scan_epilogue(ScanSharedT<QD> &sh, FrameState *fs, const KParams &kp, int b, uint32_t b0,
-                                              uint32_t b1, uint32_t qaddr, uint32_t q0, const float Lf[2],
-                                              const float Uf[2]) {
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const uint32_t nq = (qaddr - q0) / (uint32_t)(kScanThreads * 4);
-  uint32_t n0 = 0, n1 = 0;
-  for (uint32_t j = 0; j < nq; ++j) {
-    const float v = sh.pqueue[j][tid];
-    n0 += !(v > Uf[0]) ? 1u : 0u;   // also true for NaN
-    n1 += (v >= Lf[1]) ? 1u : 0u;   // +inf lands here too; harmless (it is in queue 0 as well)
-  }
-  const uint32_t pos0 = n0 ? atomicAdd(&sh.qtotal[0], n0) : 0u;
-  const uint32_t pos1 = n1 ? atomicAdd(&sh.qtotal[1], n1) : 0u;
-  b0 = warp_sum(b0);
-  b1 = warp_sum(b1);
-  if (lane == 0) { sh.red[0][warp] = b0; sh.red[1][warp] = b1; }
-  __syncthreads();
-  if (tid < 2) {
-    uint32_t r = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) r += sh.red[tid][w];
-    if (r) atomicAdd(&fs->below[tid], r);
-  } else if (tid < 4) {
-    const uint32_t t = sh.qtotal[tid - 2];
-    sh.gbase[tid - 2] = t ? atomicAdd(&fs->nqueue[tid - 2], t) : 0u;
-  }
-  __syncthreads();
-  if (nq) {
-    float *gq0 = reinterpret_cast<float *>(kp.cand) + (size_t)b * 2 * kp.cand_cap;
-    float *gq1 = gq0 + kp.cand_cap;
-    uint32_t g0 = sh.gbase[0] + pos0, g1 = sh.gbase[1] + pos1;
-    for (uint32_t j = 0; j < nq; ++j) {
-      const float v = sh.pqueue[j][tid];
-      if (!(v > Uf[0])) { if (g0 < kp.cand_cap) gq0[g0] = v; ++g0; }
-      if (v >= Lf[1]) { if (g1 < kp.cand_cap) gq1[g1] = v; ++g1; }
-    }
-  }
-}
 
 // Resized depth, up-scaling geometry: one CTA owns a kRzRows x kRzCols tile of the (H x W) map.
 // The horizontal lerp of every source row the tile needs is computed once into shared memory
@@ -260,8 +257,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_resized_tiled_kernel(KParam
   const int32_t W = kp.g.W, H = kp.g.H, sw = kp.g.w;
   float Lf[2], Uf[2];
   bracket_floats(fs, Lf, Uf);
-  if (tid < 2) sh.qtotal[tid] = 0;
-  uint32_t b0 = 0, b1 = 0;
   const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sh.pqueue[0][tid]);
   uint32_t qaddr = q0;
   const int32_t u0 = blockIdx.x * kRzCols, v0 = blockIdx.y * kRzRows;
@@ -287,6 +282,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_resized_tiled_kernel(KParam
   __syncthreads();
   {  // phase 2: vertical lerp, scan, materialise
     const int32_t c4 = (tid & 31) * 4, uu = u0 + c4, warp = tid >> 5;
+    const uint64_t pol_keep = l2_policy(false, (kp.hints & kHintResizedKeep) != 0);
     if (uu < W) {  // W % 4 == 0: the four columns are inside together
       bool cxk[4];
 #pragma unroll
@@ -310,17 +306,23 @@ __global__ void __launch_bounds__(kScanThreads) scan_resized_tiled_kernel(KParam
           o[3] = fmaf(r1.w - r0.w, ty.t, r0.w);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) scan_value(o[k], Lf, Uf, b0, b1, qaddr);
+        for (int k = 0; k < 4; ++k) scan_value(o[k], Uf[0], Lf[1], qaddr);
         float *dst = kp.resized + (size_t)b * kp.g.P + (size_t)v * W + uu;
-        *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        stg_f4_pol(dst, make_float4(o[0], o[1], o[2], o[3]), pol_keep);
       }
     }
   }
-  scan_epilogue(sh, fs, kp, b, b0, b1, qaddr, q0, Lf, Uf);
+  scan_flush(&sh.pqueue[0][0], (qaddr - q0) / (uint32_t)(kScanThreads * 4), Uf[0], Lf[1], fs, kp, b, sh.flush);
 }
 
-template <bool NATIVE>
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_ok) {
+// native-size (or already materialised) depth: one kTilePx tile per CTA
+__global__ void __launch_bounds__(kScanThreads) scan_native_kernel(KParams kp, int vec_ok) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  scan_tile<kTilePerThread>(kp, blockIdx.y, blockIdx.x, vec_ok, *reinterpret_cast<ScanTileSmem *>(s_dyn));
+}
+
+// resized depth, geometries the tiled kernel does not cover: direct gather of the four taps per pixel
+__global__ void __launch_bounds__(kScanThreads) scan_gather_kernel(KParams kp, int vec_ok) {
   __shared__ ScanShared sh;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -329,217 +331,48 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(KParams kp, int vec_
   const uint32_t n = kp.g.P;
   float Lf[2], Uf[2];
   bracket_floats(fs, Lf, Uf);
-  if (tid < 2) sh.qtotal[tid] = 0;
-  __syncthreads();
-  uint32_t b0 = 0, b1 = 0;
   const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sh.pqueue[0][tid]);
   uint32_t qaddr = q0;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kScanTile;
-
-  if (NATIVE) {
-    if (vec_ok && tile_base + (uint32_t)kScanTile <= n) {
-      // full tile: groups of 16 pixels per thread; the next group's four 16 B loads are issued
-      // before the current group is compared.  The rolled loop keeps ptxas from hoisting all 160
-      // compares ahead of their uses (which spills predicates into bit-masks).
-      constexpr int NG = kScanPerThread / 16;
-      const float *src = frame + tile_base + 4u * (uint32_t)tid;
-      float4 r[4], nx[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = ldg_stream_f4(src + (size_t)j * (4 * kScanThreads));
-#pragma unroll 1
-      for (int g = 0; g < NG; ++g) {
-        if (g + 1 < NG) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) nx[j] = ldg_stream_f4(src + (size_t)((g + 1) * 4 + j) * (4 * kScanThreads));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          scan_value(r[j].x, Lf, Uf, b0, b1, qaddr);
-          scan_value(r[j].y, Lf, Uf, b0, b1, qaddr);
-          scan_value(r[j].z, Lf, Uf, b0, b1, qaddr);
-          scan_value(r[j].w, Lf, Uf, b0, b1, qaddr);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = nx[j];
-      }
-    } else {  // last tile of a frame / unaligned frames
-#pragma unroll 1
-      for (int j = 0; j < kScanPerThread / 4; ++j) {
-        const uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
-        for (uint32_t k = 0; k < 4u; ++k)
-          if (p + k < n) scan_value(__ldg(frame + p + k), Lf, Uf, b0, b1, qaddr);
-      }
-    }
-  } else {
-    const uint32_t W = (uint32_t)kp.g.W;
+  const uint32_t W = (uint32_t)kp.g.W;
 #pragma unroll 2
-    for (int j = 0; j < kScanPerThread / 4; ++j) {
-      uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
-      if (p >= n) continue;
-      uint32_t v = p / W;
-      uint32_t u = p - v * W;
-      TapEntry ty = kp.ytab[v];
-      float val[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int j = 0; j < kScanPerThread / 4; ++j) {
+    uint32_t p = tile_base + 4u * (uint32_t)(j * kScanThreads + tid);
+    if (p >= n) continue;
+    uint32_t v = p / W;
+    uint32_t u = p - v * W;
+    TapEntry ty = kp.ytab[v];
+    float val[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (uint32_t k = 0; k < 4u; ++k) {
-        if (p + k < n) {
-          if (u >= W) {
-            u -= W;
-            v += 1;
-            ty = kp.ytab[v];
-          }
-          val[k] = bilinear_taps(frame, kp.g.w, kp.xtab[u], ty);
-          scan_value(val[k], Lf, Uf, b0, b1, qaddr);
-          u += 1;
+    for (uint32_t k = 0; k < 4u; ++k) {
+      if (p + k < n) {
+        if (u >= W) {
+          u -= W;
+          v += 1;
+          ty = kp.ytab[v];
         }
+        val[k] = bilinear_taps(frame, kp.g.w, kp.xtab[u], ty);
+        scan_value(val[k], Uf[0], Lf[1], qaddr);
+        u += 1;
       }
-      // materialise the resized map for the kernels that follow (emit, mask count, fallback)
-      float *dst = kp.resized + (size_t)b * n + p;
-      if (vec_ok && p + 3u < n) *reinterpret_cast<float4 *>(dst) = make_float4(val[0], val[1], val[2], val[3]);
-      else
-        for (uint32_t k = 0; k < 4u; ++k)
-          if (p + k < n) dst[k] = val[k];
     }
+    // materialise the resized map for the kernels that follow (emit, mask count, fallback)
+    float *dst = kp.resized + (size_t)b * n + p;
+    if (vec_ok && p + 3u < n) *reinterpret_cast<float4 *>(dst) = make_float4(val[0], val[1], val[2], val[3]);
+    else
+      for (uint32_t k = 0; k < 4u; ++k)
+        if (p + k < n) dst[k] = val[k];
   }
-
-  scan_epilogue(sh, fs, kp, b, b0, b1, qaddr, q0, Lf, Uf);
+  scan_flush(&sh.pqueue[0][0], (qaddr - q0) / (uint32_t)(kScanThreads * 4), Uf[0], Lf[1], fs, kp, b, sh.flush);
 }
 
 // ------------------------------------------------------------------------------------------
 // select_kernel
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
-  uint32_t p = 1;
-  while (p < x) p <<= 1;
-  return p;
-}
-
-__device__ void finalise_fast(FrameState *fs, uint32_t n) {
-  volatile FrameState *vfs = fs;
-  if (vfs->sel_fail) {
-    vfs->status = D2PC_FRAME_NEEDS_FALLBACK;
-    return;
-  }
-  RankPair r2 = percentile_ranks(n, D2PC_Q02), r98 = percentile_ranks(n, D2PC_Q98);
-  double p2 = lerp_percentile(key_to_float(vfs->sel_key[0]), key_to_float(vfs->sel_key[1]), r2.gamma);
-  double p98 = lerp_percentile(key_to_float(vfs->sel_key[2]), key_to_float(vfs->sel_key[3]), r98.gamma);
-  if (!(p98 > p2)) {  // degenerate percentiles need min/max: the exact path computes them
-    vfs->status = D2PC_FRAME_NEEDS_FALLBACK;
-    return;
-  }
-  NormParams np_;
-  finalise_norm(p2, p98, 0.0f, 0.0f, false, &np_);
-  np_.median = 0.0f;
-  np_.has_nonfinite = 0;
-  finish_norm(&np_);
-  fs->norm = np_;
-  __threadfence();
-  vfs->status = D2PC_FRAME_READY;
-}
-
-// visit this thread's share of a raw queue, 8 independent loads in flight per thread
-template <typename F>
-__device__ __forceinline__ void for_each_queued(const float *q, uint32_t nq, F f) {
-  const uint32_t stride = blockDim.x;
-  uint32_t i = threadIdx.x;
-  for (; i + 7u * stride < nq; i += 8u * stride) {
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(q + i + (uint32_t)k * stride);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f(v[k]);
-  }
-  for (; i < nq; i += stride) f(__ldg(q + i));
-}
-
-__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(KParams kp) {
-  extern __shared__ uint32_t s_hist[];  // 2 << kSelBits words
-  __shared__ uint32_t s_res[2 * 2 + 40];
-  __shared__ uint32_t s_c[5];  // eqL, inside, eqU, non-finite, NaN
-  const int br = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  FrameState *fs = kp.state + b;
-  const uint32_t n = kp.g.P;
-  const uint32_t qcap = kp.cand_cap;
-  const float *q = reinterpret_cast<const float *>(kp.cand) + ((size_t)b * 2 + br) * qcap;
-  const uint32_t nqueue = fs->nqueue[br];
-  const uint32_t nq = min(nqueue, qcap);
-  const uint32_t L = fs->brL[br], U = fs->brU[br];
-  float Lf2[2], Uf2[2];
-  bracket_floats(fs, Lf2, Uf2);
-  const float Lf = Lf2[br], Uf = Uf2[br];
-  if (tid < 5) s_c[tid] = 0;
-  __syncthreads();
-  {  // pass 0: classify the queued values against this bracket
-    uint32_t c_eqL = 0, c_in = 0, c_eqU = 0, c_nf = 0, c_nan = 0;
-    for_each_queued(q, nq, [&](float v) {
-      if (!(fabsf(v) < __int_as_float(0x7F800000))) { c_nf++; if (v != v) c_nan++; }
-      else if (v >= Lf && v <= Uf) {
-        if (v == Lf) c_eqL++;
-        else if (v < Uf) c_in++;
-        else c_eqU++;
-      }
-    });
-    c_eqL = warp_sum(c_eqL); c_in = warp_sum(c_in); c_eqU = warp_sum(c_eqU);
-    c_nf = warp_sum(c_nf); c_nan = warp_sum(c_nan);
-    if ((tid & 31) == 0) {
-      if (c_eqL) atomicAdd(&s_c[0], c_eqL);
-      if (c_in) atomicAdd(&s_c[1], c_in);
-      if (c_eqU) atomicAdd(&s_c[2], c_eqU);
-      if (c_nf) atomicAdd(&s_c[3], c_nf);
-      if (c_nan) atomicAdd(&s_c[4], c_nan);
-    }
-  }
-  __syncthreads();
-  const uint32_t below = fs->below[br], eqL = s_c[0], nin = s_c[1], eqU = s_c[2];
-  // a non-finite value anywhere in the frame shows up in queue 0; both CTAs must agree to fail,
-  // which the shared sel_fail flag takes care of
-  bool fail = (s_c[3] != 0u) || (nqueue > qcap) || (fs->sample_ok == 0u) || (kp.force_fallback != 0);
-  RankPair rp = percentile_ranks(n, br ? D2PC_Q98 : D2PC_Q02);
-  long long need[2] = {-1, -1};
-  uint32_t key[2] = {0u, 0u};
-  for (int t = 0; t < 2; ++t) {
-    uint32_t r = t ? rp.hi : rp.lo;
-    if (r < below) { fail = true; continue; }
-    uint32_t r1 = r - below;
-    if (r1 < eqL) { key[t] = L; continue; }
-    uint32_t r2 = r1 - eqL;
-    if (r2 < nin) { need[t] = r2; continue; }
-    uint32_t r3 = r2 - nin;
-    if (r3 < eqU) { key[t] = U; continue; }
-    fail = true;
-  }
-  const bool any_need = need[0] >= 0 || need[1] >= 0;
-
-  if (!fail && any_need) {  // uniform over the CTA
-    // strictly inside (L, U) in float order; -0.0 == +0.0 there, so when a bound is a zero the
-    // other zero's key can sit one step outside the key interval: widen the key range by one
-    const uint32_t lo0 = L > 0u ? L - 1u : 0u;
-    const uint32_t hi0 = U < 0xFFFFFFFFu ? U + 1u : U;
-    uint32_t rk[2], ok_[2];
-    for (int t = 0; t < 2; ++t) rk[t] = (uint32_t)(need[t] >= 0 ? need[t] : need[1 - t]);
-    const bool ok = block_hist_select<2, kSelBits>([&](auto f) {
-      for_each_queued(q, nq, [&](float v) {
-        if (v > Lf && v < Uf) f(float_to_key(v));
-      });
-    }, lo0, hi0, rk, ok_, s_hist, s_res);
-    if (!ok) fail = true;
-    for (int t = 0; t < 2; ++t)
-      if (need[t] >= 0) key[t] = ok_[t];
-  }
-
-  if (tid == 0) {
-    fs->sel_key[2 * br + 0] = key[0];
-    fs->sel_key[2 * br + 1] = key[1];
-    fs->eqL[br] = eqL; fs->inside[br] = nin; fs->eqU[br] = eqU;
-    if (br == 0) { fs->n_nonfinite = s_c[3]; fs->n_nan = s_c[4]; }  // non-finite values live in queue 0
-    if (fail) atomicOr(&fs->sel_fail, 1u);
-    __threadfence();
-    uint32_t ticket = atomicAdd(&fs->sel_done, 1u);
-    if (ticket == 1u) {
-      __threadfence();
-      finalise_fast(fs, n);
-    }
-  }
+__global__ void __launch_bounds__(kSelectThreads, 2) select_kernel(KParams kp) {
+  extern __shared__ uint32_t s_sel[];  // kSelectSmemWords
+  __shared__ SelectSmall ss;
+  select_bracket(kp, blockIdx.y, blockIdx.x, s_sel, ss);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -777,42 +610,54 @@ static int check_ws(const D2pcConfig *cfg, const void *ws, size_t ws_bytes) {
   return D2PC_OK;
 }
 
-extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
-                                  size_t workspace_bytes, void *stream) {
-  int rc = check_ws(cfg, d_workspace, workspace_bytes);
-  if (rc) return rc;
-  if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
-  cudaStream_t st = (cudaStream_t)stream;
-  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+// sample -> scan -> select for the nb frames of a (sliced) parameter block.  The tap tables of a resized
+// depth are per call, not per slice: the caller runs taps_launch once.
+namespace d2pc {
+
+int taps_launch(const KParams &kp, cudaStream_t st) {
+  if (kp.g.native || resize_is_generic(kp.g.h, kp.g.w)) return D2PC_OK;
+  taps_kernel<<<(kp.g.W + kp.g.H + 255) / 256, 256, 0, st>>>(kp);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
+int stats_prepare() {
+  const size_t sample_smem = (size_t)(4u << kSelBits) * sizeof(uint32_t);  // 64 KB (general selection)
+  const size_t select_smem = (size_t)kSelectSmemWords * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(scan_native_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanTileSmem));
+  if (e != cudaSuccess) return record_cuda_error(e);
+  return D2PC_OK;
+}
+
+int stats_launch(KParams kp, cudaStream_t st, int phases) {
+  const int nb = kp.batch;
   if (!kp.g.native && resize_is_generic(kp.g.h, kp.g.w)) {
     const uint32_t blocks = (kp.g.P + 255u) / 256u;
-    resize_generic_kernel<<<dim3(blocks < 148u * 8u ? blocks : 148u * 8u, cfg->batch), 256, 0, st>>>(kp);
-    D2PC_CHECK_LAUNCH();
+    if (phases & kStatsSample) {
+      resize_generic_kernel<<<dim3(blocks < 148u * 8u ? blocks : 148u * 8u, nb), 256, 0, st>>>(kp);
+      D2PC_CHECK_LAUNCH();
+    }
     kp = per_pixel_view(kp);   // the statistics read the materialised map
-    d_depth = kp.depth;
   }
-  const size_t sample_smem = (size_t)(4u << kSelBits) * sizeof(uint32_t);  // 64 KB
-  const size_t select_smem = (size_t)(2u << kSelBits) * sizeof(uint32_t);  // 32 KB
-  {
-    cudaError_t e = kp.g.native
-        ? cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem)
-        : cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem);
-    if (e != cudaSuccess) return record_cuda_error(e);
-  }
-  const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)d_depth & 15u) == 0u);
-  dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, cfg->batch);
-  const size_t scan_smem_bytes = 0;
-  if (!kp.g.native) {
-    taps_kernel<<<(kp.g.W + kp.g.H + 255) / 256, 256, 0, st>>>(kp);
+  const size_t sample_smem = (size_t)(4u << kSelBits) * sizeof(uint32_t);
+  const size_t select_smem = (size_t)kSelectSmemWords * sizeof(uint32_t);
+  const int vec_ok = ((kp.g.P & 3u) == 0u) && (((uintptr_t)kp.depth & 15u) == 0u);
+  dim3 scan_grid((kp.g.P + kScanTile - 1) / kScanTile, nb);
+  if (phases & kStatsSample) {
+    if (kp.g.native) sample_kernel<true><<<nb, kSelThreads, sample_smem, st>>>(kp);
+    else sample_kernel<false><<<nb, kSelThreads, sample_smem, st>>>(kp);
     D2PC_CHECK_LAUNCH();
   }
+  if (!(phases & kStatsScanSelect)) return D2PC_OK;
   if (kp.g.native) {
-    sample_kernel<true><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
-    D2PC_CHECK_LAUNCH();
-    scan_kernel<true><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, vec_ok);
+    scan_native_kernel<<<dim3((kp.g.P + kTilePx - 1) / kTilePx, nb), kScanThreads, sizeof(ScanTileSmem), st>>>(kp, vec_ok);
   } else {
-    sample_kernel<false><<<cfg->batch, kSelThreads, sample_smem, st>>>(kp);
-    D2PC_CHECK_LAUNCH();
     // tiled kernel: needs 16 B-aligned rows of the resized map and every tile's source rows in shared memory
     bool tiled = (kp.g.W & 3) == 0;
     for (int32_t v0 = 0; tiled && v0 < kp.g.H; v0 += kRzRows) {
@@ -821,16 +666,38 @@ extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, v
       if (t1.i1 - t0.i0 + 1 > kRzSrcRows) tiled = false;
     }
     if (tiled) {
-      dim3 tg((kp.g.W + kRzCols - 1) / kRzCols, (kp.g.H + kRzRows - 1) / kRzRows, cfg->batch);
+      dim3 tg((kp.g.W + kRzCols - 1) / kRzCols, (kp.g.H + kRzRows - 1) / kRzRows, nb);
       scan_resized_tiled_kernel<<<tg, kScanThreads, 0, st>>>(kp);
     } else {
-      scan_kernel<false><<<scan_grid, kScanThreads, scan_smem_bytes, st>>>(kp, (kp.g.P & 3u) == 0u ? 1 : 0);
+      scan_gather_kernel<<<scan_grid, kScanThreads, 0, st>>>(kp, (kp.g.P & 3u) == 0u ? 1 : 0);
     }
   }
   D2PC_CHECK_LAUNCH();
-  select_kernel<<<dim3(2, cfg->batch), kSelThreads, select_smem, st>>>(kp);
+  select_kernel<<<dim3(2, nb), kSelectThreads, select_smem, st>>>(kp);
   D2PC_CHECK_LAUNCH();
   return D2PC_OK;
+}
+
+int status_launch(const KParams &kp, int32_t *d_status, int32_t *d_any, cudaStream_t st) {
+  status_kernel<<<1, 256, 0, st>>>(kp, d_status, d_any);
+  D2PC_CHECK_LAUNCH();
+  return D2PC_OK;
+}
+
+int check_workspace(const D2pcConfig *cfg, const void *ws, size_t ws_bytes) { return check_ws(cfg, ws, ws_bytes); }
+
+}  // namespace d2pc
+
+extern "C" int d2pc_stats_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_workspace,
+                                  size_t workspace_bytes, void *stream) {
+  int rc = check_ws(cfg, d_workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!d_depth) return D2PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  KParams kp = make_kparams(*cfg, d_depth, d_workspace);
+  if ((rc = stats_prepare()) != D2PC_OK) return rc;
+  if ((rc = taps_launch(kp, st)) != D2PC_OK) return rc;
+  return stats_launch(kp, st, kStatsSample | kStatsScanSelect);
 }
 
 extern "C" int d2pc_stats_fallback_enqueue(const D2pcConfig *cfg, const float *d_depth,
@@ -868,9 +735,7 @@ extern "C" int d2pc_frame_status(const D2pcConfig *cfg, const void *d_workspace,
   if (rc) return rc;
   if (!d_workspace) return D2PC_ERR_INVALID_ARGUMENT;
   KParams kp = make_kparams(*cfg, nullptr, (void *)d_workspace);
-  status_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(kp, d_status, d_any_fallback);
-  D2PC_CHECK_LAUNCH();
-  return D2PC_OK;
+  return status_launch(kp, d_status, d_any_fallback, (cudaStream_t)stream);
 }
 
 extern "C" int d2pc_frame_params(const D2pcConfig *cfg, const void *d_workspace,

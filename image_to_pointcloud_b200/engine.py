@@ -100,6 +100,7 @@ class FrameEngine:
         assert self.workspace.data_ptr() % 256 == 0
         self._voxel_table = None
         self._smooth_scratch = None
+        self._path = None
 
     # ---- configuration -------------------------------------------------------------------
     def make_config(self, density: str = "high", invert: bool = True, depth_scale: float = 10.0,
@@ -151,30 +152,77 @@ class FrameEngine:
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         return s.cuda_stream
 
+    def _call(self, name: str, *args) -> None:
+        """One C-ABI call with the engine's device current (the library launches on the current device and
+        sets kernel attributes there), whatever device the caller's thread has selected."""
+        with torch.cuda.device(self.device):
+            check(getattr(self.lib, name)(*args), name)
+
     # ---- asynchronous pieces (enqueue only, no host sync) ---------------------------------
     def enqueue_stats(self, cfg: D2pcConfig, depth: torch.Tensor, stream=None) -> None:
-        check(self.lib.d2pc_stats_enqueue(C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
-                                          self.workspace_bytes, self._stream(stream)), "d2pc_stats_enqueue")
+        self._call("d2pc_stats_enqueue", C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
+                   self.workspace_bytes, self._stream(stream))
 
     def enqueue_stats_fallback(self, cfg: D2pcConfig, depth: torch.Tensor, stream=None) -> None:
-        check(self.lib.d2pc_stats_fallback_enqueue(C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
-                                                   self.workspace_bytes, self._stream(stream)),
-              "d2pc_stats_fallback_enqueue")
+        self._call("d2pc_stats_fallback_enqueue", C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
+                   self.workspace_bytes, self._stream(stream))
 
     def enqueue_status(self, cfg: D2pcConfig, stream=None) -> None:
         """status words -> self._status, any-fallback flag -> pinned host word (async copy)."""
-        check(self.lib.d2pc_frame_status(C.byref(cfg), self.workspace.data_ptr(), self._status.data_ptr(),
-                                         self._any.data_ptr(), self._stream(stream)), "d2pc_frame_status")
+        self._call("d2pc_frame_status", C.byref(cfg), self.workspace.data_ptr(), self._status.data_ptr(),
+                   self._any.data_ptr(), self._stream(stream))
+        self._copy_flag(stream)
+
+    def _copy_flag(self, stream=None) -> None:
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(s):
+        with torch.cuda.device(self.device), torch.cuda.stream(s):
             self._any_host.copy_(self._any, non_blocking=True)
 
     def enqueue_emit(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],
                      xyz: torch.Tensor, rgb: torch.Tensor, count: torch.Tensor,
                      bounds: Optional[torch.Tensor] = None, stream=None) -> None:
-        check(self.lib.d2pc_emit_enqueue(C.byref(cfg), depth.data_ptr(), _ptr(bgr), self.workspace.data_ptr(),
-                                         self.workspace_bytes, xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(),
-                                         _ptr(bounds), self._stream(stream)), "d2pc_emit_enqueue")
+        self._call("d2pc_emit_enqueue", C.byref(cfg), depth.data_ptr(), _ptr(bgr), self.workspace.data_ptr(),
+                   self.workspace_bytes, xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(), _ptr(bounds),
+                   self._stream(stream))
+
+    # ---- the whole path as one sub-batch pipeline (csrc/d2pc_path.cu) -----------------------
+    def enqueue_path(self, cfg: D2pcConfig, depth: torch.Tensor, bgr: Optional[torch.Tensor],
+                     xyz: torch.Tensor, rgb: torch.Tensor, count: torch.Tensor,
+                     bounds: Optional[torch.Tensor] = None, stream=None, *, sub_batch: Optional[int] = None,
+                     lookahead: int = 0, graph: bool = False, flags: int = 0) -> None:
+        """statistics + status + emit of the batch, pipelined over sub-batches so that each depth map is read
+        from HBM once (the statistics of sub-batch k+1 overlap the emit of sub-batch k).  The per-frame status
+        words land in ``self._status`` and the any-fallback flag in the pinned ``self._any_host`` (valid after
+        the stream has been synchronised), like ``enqueue_status``.  ``graph=True`` replays a cached CUDA graph
+        while the arguments repeat (steady-state batches on the same buffers)."""
+        if self._path is None:
+            h = C.c_void_p()
+            self._call("d2pc_path_create", C.byref(h))
+            self._path = h
+        if sub_batch is None:
+            sub_batch = self.default_sub_batch()
+        self._call("d2pc_path_enqueue", self._path, C.byref(cfg), depth.data_ptr(), _ptr(bgr),
+                   self.workspace.data_ptr(), self.workspace_bytes, xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(),
+                   _ptr(bounds), self._status.data_ptr(), self._any.data_ptr(), int(sub_batch), int(lookahead),
+                   int(flags) | (_lib.PATH_GRAPH if graph else 0), self._stream(stream))
+        self._copy_flag(stream)
+
+    L2_BUDGET_BYTES = 40 << 20  # per-pixel depth of one sub-batch (two are in flight) -- measured on B200
+
+    def default_sub_batch(self) -> int:
+        """Frames per pipeline stage such that two stages' per-pixel depth maps stay in the 126 MB L2 next to
+        the streaming traffic."""
+        per_frame = self.img_h * self.img_w * 4
+        return max(1, min(self.batch, self.L2_BUDGET_BYTES // per_frame))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_path", None) is not None:
+                with torch.cuda.device(self.device):
+                    self.lib.d2pc_path_destroy(self._path)
+                self._path = None
+        except Exception:
+            pass
 
     def enqueue_emit_smooth(self, cfg: D2pcConfig, smooth_ksize, depth: torch.Tensor,
                             bgr: Optional[torch.Tensor], xyz: torch.Tensor, rgb: torch.Tensor,
@@ -189,11 +237,10 @@ class FrameEngine:
             if self._smooth_scratch is None or self._smooth_scratch.numel() < nbytes.value:
                 self._smooth_scratch = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
         arr = (C.c_double * len(coeffs))(*coeffs)
-        check(self.lib.d2pc_emit_smooth_enqueue(C.byref(cfg), depth.data_ptr(), _ptr(bgr), self.workspace.data_ptr(),
-                                                self.workspace_bytes, len(coeffs), arr,
-                                                self._smooth_scratch.data_ptr(), self._smooth_scratch.numel(),
-                                                xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(), _ptr(bounds),
-                                                self._stream(stream)), "d2pc_emit_smooth_enqueue")
+        self._call("d2pc_emit_smooth_enqueue", C.byref(cfg), depth.data_ptr(), _ptr(bgr), self.workspace.data_ptr(),
+                   self.workspace_bytes, len(coeffs), arr, self._smooth_scratch.data_ptr(),
+                   self._smooth_scratch.numel(), xyz.data_ptr(), rgb.data_ptr(), count.data_ptr(), _ptr(bounds),
+                   self._stream(stream))
 
     # ---- f2 depth preview ----------------------------------------------------------------
     def depth_preview(self, depth: torch.Tensor, invert: bool = True, stream=None) -> torch.Tensor:
@@ -214,9 +261,8 @@ class FrameEngine:
             out = torch.empty((self.batch, self.dep_h, self.dep_w, 3), dtype=torch.uint8, device=self.device)
 
         def run():
-            check(self.lib.d2pc_preview_enqueue(C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
-                                                self.workspace_bytes, self._lut.data_ptr(), out.data_ptr(),
-                                                s.cuda_stream), "d2pc_preview_enqueue")
+            self._call("d2pc_preview_enqueue", C.byref(cfg), depth.data_ptr(), self.workspace.data_ptr(),
+                       self.workspace_bytes, self._lut.data_ptr(), out.data_ptr(), s.cuda_stream)
         self.enqueue_stats(cfg, depth, s)
         self.enqueue_status(cfg, s)
         run()
@@ -254,11 +300,21 @@ class FrameEngine:
             if after_emit is not None:
                 with torch.cuda.stream(s):
                     after_emit(xyz, rgb, count, bounds)
-        self.enqueue_stats(cfg, depth, s)
-        self.enqueue_status(cfg, s)
-        emit()
+        if smooth_ksize is None:
+            # one sub-batch pipeline: statistics of sub-batch k+1 under the emit of sub-batch k
+            self.enqueue_path(cfg, depth, bgr, xyz, rgb, count, bounds, s)
+            if after_emit is not None:
+                with torch.cuda.stream(s):
+                    after_emit(xyz, rgb, count, bounds)
+        else:
+            self.enqueue_stats(cfg, depth, s)
+            self.enqueue_status(cfg, s)
+            emit()
         s.synchronize()
         if int(self._any_host[0]) != 0:
+            # frames the fast statistics could not finish exactly: batch-wide statistics again (the pipeline
+            # keeps only the last sub-batches' resized maps), the exact fallback for the flagged frames, emit
+            self.enqueue_stats(cfg, depth, s)
             self.enqueue_stats_fallback(cfg, depth, s)
             emit()
             s.synchronize()
@@ -268,8 +324,7 @@ class FrameEngine:
         """Per-frame normalisation parameters as the device computed them (tests / debugging)."""
         with torch.cuda.device(self.device):
             buf = torch.zeros(self.batch * C.sizeof(D2pcFrameParams), dtype=torch.uint8, device=self.device)
-        check(self.lib.d2pc_frame_params(C.byref(cfg), self.workspace.data_ptr(), buf.data_ptr(),
-                                         self._stream(None)), "d2pc_frame_params")
+        self._call("d2pc_frame_params", C.byref(cfg), self.workspace.data_ptr(), buf.data_ptr(), self._stream(None))
         raw = buf.cpu().numpy().tobytes()
         out = []
         for b in range(self.batch):
@@ -292,19 +347,17 @@ class FrameEngine:
         with torch.cuda.device(self.device):
             if self._voxel_table is None or self._voxel_table.numel() < nbytes.value:
                 self._voxel_table = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
-                check(self.lib.d2pc_voxel_table_init(C.byref(cfg), self._voxel_table.data_ptr(),
-                                                     self._voxel_table.numel(), self._stream(stream)),
-                      "d2pc_voxel_table_init")
+                self._call("d2pc_voxel_table_init", C.byref(cfg), self._voxel_table.data_ptr(),
+                           self._voxel_table.numel(), self._stream(stream))
             vxyz = torch.empty_like(res.xyz)
             vrgb = torch.empty_like(res.rgb)
             vidx = torch.empty(res.xyz.shape, dtype=torch.int32, device=self.device) if want_index else None
             vcount = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
             verr = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
-        check(self.lib.d2pc_voxel_enqueue(C.byref(cfg), float(voxel_size), res.xyz.data_ptr(), res.rgb.data_ptr(),
-                                          res.count.data_ptr(), res.bounds.data_ptr(),
-                                          self._voxel_table.data_ptr(), self._voxel_table.numel(),
-                                          vxyz.data_ptr(), vrgb.data_ptr(), _ptr(vidx), vcount.data_ptr(),
-                                          verr.data_ptr(), self._stream(stream)), "d2pc_voxel_enqueue")
+        self._call("d2pc_voxel_enqueue", C.byref(cfg), float(voxel_size), res.xyz.data_ptr(), res.rgb.data_ptr(),
+                   res.count.data_ptr(), res.bounds.data_ptr(), self._voxel_table.data_ptr(),
+                   self._voxel_table.numel(), vxyz.data_ptr(), vrgb.data_ptr(), _ptr(vidx), vcount.data_ptr(),
+                   verr.data_ptr(), self._stream(stream))
         if check_error:
             e = verr.cpu()
             if bool((e == 2).any()):
@@ -347,8 +400,8 @@ class BatchStream:
         if self.k >= 2:
             self.s_stats.wait_event(self.emit_done[i])  # the workspace is free once emit(k-2) is done
         eng.enqueue_stats(self.cfg, depth, self.s_stats)
-        check(eng.lib.d2pc_frame_status(C.byref(self.cfg), eng.workspace.data_ptr(), eng._status.data_ptr(),
-                                        eng._any.data_ptr(), self.s_stats.cuda_stream), "d2pc_frame_status")
+        eng._call("d2pc_frame_status", C.byref(self.cfg), eng.workspace.data_ptr(), eng._status.data_ptr(),
+                  eng._any.data_ptr(), self.s_stats.cuda_stream)
         with torch.cuda.device(self.device):
             flag = torch.zeros(1, dtype=torch.int32, pin_memory=True)
             with torch.cuda.stream(self.s_stats):

@@ -145,6 +145,36 @@ int d2pc_emit_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t
                       void *d_workspace, size_t workspace_bytes, float *d_xyz, float *d_rgb,
                       uint32_t *d_count, float *d_bounds, void *stream);
 
+/* The whole path (d2pc_stats_enqueue + d2pc_frame_status + d2pc_emit_enqueue) of a batch as ONE software
+ * pipeline over sub-batches of `sub_batch` frames (csrc/d2pc_path.cu): the statistics of sub-batch k+1 run on
+ * an auxiliary high-priority stream while the emit of sub-batch k streams its rows out, with L2 eviction hints
+ * such that every depth map (or materialised resized map) is read from HBM once.  Results are identical to
+ * the two-phase calls.  Frames the fast statistics cannot finish exactly are left out and flagged in d_status /
+ * *d_any_fallback (either may be NULL) exactly like d2pc_frame_status; the host then runs the two-phase calls
+ * with d2pc_stats_fallback_enqueue in between (python: FrameEngine.process).
+ *   D2pcPath     opaque handle: the auxiliary stream, the events of the fork / join and a cached CUDA graph.
+ *                The one exception to "the library allocates nothing": created and destroyed by the caller,
+ *                bound to the device that was current at creation, used by one host thread at a time.
+ *   sub_batch    frames per pipeline stage (<= 0 or >= batch: one stage, no overlap)
+ *   lookahead    sub-batches the statistics may run ahead of the emit (>= 1)
+ *   flags        D2PC_PATH_GRAPH: capture the step into a CUDA graph once and replay it while all arguments
+ *                repeat (steady-state batches); D2PC_PATH_NO_OVERLAP / D2PC_PATH_NO_L2_HINTS: measurement aids */
+typedef struct D2pcPath D2pcPath;
+#define D2PC_PATH_GRAPH 1
+#define D2PC_PATH_NO_OVERLAP 2
+#define D2PC_PATH_NO_L2_HINTS 4
+#define D2PC_PATH_STREAMS 8
+int d2pc_path_create(D2pcPath **path);
+void d2pc_path_destroy(D2pcPath *path);
+int d2pc_path_enqueue(D2pcPath *path, const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
+                      void *d_workspace, size_t workspace_bytes, float *d_xyz, float *d_rgb, uint32_t *d_count,
+                      float *d_bounds, int32_t *d_status, int32_t *d_any_fallback, int32_t sub_batch,
+                      int32_t lookahead, int32_t flags, void *stream);
+
+/* measurement aid: byte offset in the workspace of the persistent kernel's per-frame trace (8 x uint64 ns per frame:
+ * first scan tile, last scan tile, selection start / end of bracket 0 and 1, first emit tile, last emit tile) */
+int d2pc_path_trace_offset(const D2pcConfig *cfg, size_t *offset);
+
 /* a6 + a9..a11: the same emission with the optional smoothing of app.py:208-214 switched on:
  * cv2.GaussianBlur(d, (k, k), 0) on the normalised (and inverted) map before the back-projection.
  *   ksize      k = max(3, smooth_ksize // 2 * 2 + 1), odd, <= D2PC_MAX_SMOOTH_KSIZE
