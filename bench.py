@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  (CPU arm, rank 0 only)
 
-A *step* is one pass of the whole hot path (exact percentile statistics + fused emit) over one
-batch of synthetic frames.  Workload at every N: BASELINE.json configs[1] -- 1920x1080 frames,
+A *step* is one pass of the whole hot path (exact percentile statistics + fused emit, one library
+call: d2pc_path_enqueue, replayed as a CUDA graph) over one batch of synthetic frames.  Workload at every N: BASELINE.json configs[1] -- 1920x1080 frames,
 native-size float32 depth + uint8 BGR, density "high" (stride 1), invert, depth_scale 10, every
 point kept (the reference has no mask) -- ``--batch`` frames per GPU per step (weak scaling:
 frames are independent, sharded by frame, no collective on the data path).
@@ -15,8 +15,11 @@ e2e     same metric through the host API (HostFramePipeline.run_pinned): pinned 
         pinned HOST buffers out, H2D and D2H inside the timed region.
 roofline  the dominant kernel (emit): algorithmic bytes (4 B depth + 3 B BGR + 24 B out per
         point) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline  the oracle's loop-faithful port of the reference (backend/app.py:228-246) timed on
-        one host core on a bounded sample (rank 0, N = 1 only).
+cpu_baseline  the UNMODIFIED reference function (baseline/_ref/backend/app.py, copied from
+        /root/reference by __graft_entry__.build(); the oracle's loop-faithful port if that copy is
+        absent) timed on one host core on a bounded sample (rank 0, N = 1 only).
+extras  (N = 1) the other BASELINE.json configurations, device-resident: 1080p with a DA-v2-sized
+        depth map, 4K native, configs[2] (4K + z-range + 5 mm voxels), configs[4] (voxel sweep).
 """
 from __future__ import annotations
 
@@ -47,7 +50,8 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=32, help="frames per e2e step (0: same as --batch)")
     ap.add_argument("--chunk", type=int, default=8, help="frames per pipeline chunk in the e2e path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time mask / resized / 4K variants")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (N = 1)")
+    ap.add_argument("--extras-full", action="store_true", help="also writers / outlier removal / single-call latency")
     return ap.parse_args()
 
 
@@ -165,23 +169,45 @@ def synth_frames_device(n, device, seed0):
 # ----------------------------------------------------------------------------------------------
 # CPU arm
 # ----------------------------------------------------------------------------------------------
-def _cpu_loop_job(job):
-    """One bounded sample: the loop-faithful port on an (h x w) crop-sized frame."""
-    h, w, seed = job
+_REF_FN = None       # set in the parent before the worker pool forks
+_REF_KIND = "port"
+
+
+def _load_cpu_reference():
+    """The stock reference function when its copy travelled with the repo, else the oracle's port."""
+    global _REF_FN, _REF_KIND
+    if _REF_FN is not None:
+        return _REF_FN, _REF_KIND
+    try:
+        from baseline import ref_arm
+        if ref_arm.available():
+            _REF_FN, _REF_KIND = ref_arm.load(), "reference"
+            return _REF_FN, _REF_KIND
+    except Exception as e:  # missing dependency of app.py on this box: say so, use the port
+        print("reference copy not loadable (%s): using the oracle's port" % e, file=sys.stderr)
     from oracle import d2pc_oracle as O
+    _REF_FN, _REF_KIND = O.depth_to_point_cloud_loop, "port"
+    return _REF_FN, _REF_KIND
+
+
+def _cpu_loop_job(job):
+    """One bounded sample: the reference function on an (h x w) native-depth frame."""
+    h, w, seed = job
     from tests import cases
+    fn, _ = _load_cpu_reference()
     img = cases.make_image(h, w, seed)
     dep = cases.make_depth(h, w, seed, "uniform")
     t0 = time.perf_counter()
-    p, c = O.depth_to_point_cloud_loop(img, dep, density="high")
+    p, c = fn(img, dep, density="high")
     return len(p), time.perf_counter() - t0
 
 
 def cpu_baseline_single_core():
-    """Rank 0, N = 1: one core, a quarter-height 1080p frame (270 x 1920 = 518 400 points,
-    ~3-4 s); the per-point cost of the Python loop does not depend on the frame size."""
+    """Rank 0, N = 1: one core, a quarter-height 1080p frame (270 x 1920 = 518 400 points, ~1.5 s); the
+    per-point cost of the reference's Python loop does not depend on the frame size."""
     from oracle import d2pc_oracle as O
     from tests import cases
+    fn, kind = _load_cpu_reference()
     h, w = 270, 1920
     n, dt = _cpu_loop_job((h, w, 1))
     img = cases.make_image(IMG_H, IMG_W, 1)
@@ -189,22 +215,25 @@ def cpu_baseline_single_core():
     t0 = time.perf_counter()
     O.depth_to_point_cloud(img, dep, density="high")
     dv = time.perf_counter() - t0
-    return {"value": round(n / dt / 1e6, 4), "unit": UNIT, "cores": 1, "kind": "port",
+    what = ("the unmodified reference depth_to_point_cloud (baseline/_ref/backend/app.py:174-250)" if kind == "reference"
+            else "oracle.depth_to_point_cloud_loop (line-for-line port of app.py:183-246)")
+    return {"value": round(n / dt / 1e6, 4), "unit": UNIT, "cores": 1, "kind": kind,
             "cores_available": os.cpu_count(),
-            "sample": "oracle.depth_to_point_cloud_loop (line-for-line port of app.py:183-246) on one "
-                      "270x1920 native-depth frame, density=high (%d points, %.2f s)" % (n, dt),
+            "sample": "%s on one 270x1920 native-depth frame, density=high (%d points, %.2f s)" % (what, n, dt),
             "vectorised_numpy_port_mpoints_s": round(IMG_H * IMG_W / dv / 1e6, 3)}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path.  /root/reference does not
-    exist on the GPU box and the reference is Python (nothing to compile into oracle/_ref), so this
-    is the oracle's loop-faithful port, one process per host core, each step one bounded sample
-    (a 135x1920 band-sized frame per core)."""
+    """--impl reference: the reference's own CPU implementation of the path -- the unmodified
+    backend/app.py::depth_to_point_cloud from baseline/_ref (the oracle's port only if that copy is missing) --
+    on every host core: one forked process per core, each step one bounded sample per core (a 135 x 1920
+    native-depth frame = 1/8 of a 1080p frame; the per-point cost of the Python loop does not depend on the
+    frame size)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    fn, kind = _load_cpu_reference()   # imported once here; the workers are forked from this process
     cores = os.cpu_count() or 1
     h, w = 135, 1920
     ctx = mp.get_context("fork")
@@ -218,15 +247,28 @@ def run_reference_arm(args):
             pts += sum(n for n, _ in pool.map(_cpu_loop_job, jobs(args.warmup + s)))
         dt = time.perf_counter() - t0
     val = pts / dt / 1e6
+    cfg = config_dict(args, args.gpus)
+    # what this arm really processed per step: a bounded sample of the same workload (same frame content, knobs
+    # and per-point work), sized for the CPU -- not the GPU arm's 128 frames per step
+    eq = round(cores * h * w / (IMG_H * IMG_W), 3)
+    cfg["frames_per_gpu_per_step"] = eq
+    cfg["global_frames_per_step"] = eq
+    cfg["parallelism"] = "%d host processes, one bounded sample each per step" % cores
+    cfg.pop("l2_hygiene", None)
+    cfg["reference_arm_step"] = {"frames": cores, "frame_shape": [h, w], "points": cores * h * w,
+                                 "equivalent_1080p_frames": round(cores * h * w / (IMG_H * IMG_W), 3),
+                                 "processes": cores, "implementation": kind}
+    what = ("unmodified reference backend/app.py::depth_to_point_cloud" if kind == "reference"
+            else "oracle.depth_to_point_cloud_loop (port)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_dict(args, args.gpus),
+        "data": "synthetic", "config": cfg,
         "images_per_s": round(val * 1e6 / (IMG_H * IMG_W), 4),
-        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "per step and core: oracle.depth_to_point_cloud_loop on one 135x1920 "
-                                   "native-depth frame (1/8 of a 1080p frame), density=high"},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "per step and core: %s on one 135x1920 native-depth frame (1/8 of a 1080p "
+                                   "frame), density=high" % what},
         "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -275,10 +317,9 @@ def run_ours(args):
     n_points = eng.points_per_frame(cfg)
 
     def step():
-        eng.enqueue_stats(cfg, depth, stream)
-        eng.enqueue_status(cfg, stream)
-        eng.enqueue_emit(cfg, depth, bgr, xyz, rgb, count, None, stream)
-    launches_per_step = 3 + 1 + 1  # sample, scan, select | status | emit
+        # statistics + status + emit in one library call, replayed as a CUDA graph
+        eng.enqueue_path(cfg, depth, bgr, xyz, rgb, count, None, stream, graph=True)
+    launches_per_step = 3 + 1 + 1  # sample, scan, select | emit | status
 
     def barrier():
         if world > 1:
@@ -302,6 +343,19 @@ def run_ours(args):
         barrier()
     ms_total = ev0.elapsed_time(ev1)
     assert int(eng._any_host[0]) == 0
+    if rank == 0:
+        # what was timed is checked against the oracle: one frame of the timed output, bit for bit
+        import warnings
+
+        import numpy as np
+        from oracle import d2pc_oracle as O  # checker only
+        fchk = B // 2
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            po, co = O.depth_to_point_cloud(bgr[fchk].cpu().numpy(), depth[fchk].cpu().numpy(), density="high")
+        got_p, got_c = xyz[fchk].cpu().numpy(), rgb[fchk].cpu().numpy()
+        assert np.array_equal(got_p.view(np.uint32), po.view(np.uint32)), "timed frame: xyz differs from the oracle"
+        assert np.array_equal(got_c, co), "timed frame: rgb differs from the oracle"
 
     # dominant kernel alone (emit), CUDA events on the same stream, same buffers (> L2)
     emit_iters = max(K, 10)
@@ -351,8 +405,8 @@ def run_ours(args):
     ms_total, e2e_s, emit_ms, stats_ms = (float(x) for x in t.cpu())
 
     extras = {}
-    if args.extras and rank == 0:
-        extras = run_extras(m, device)
+    if world == 1 and rank == 0 and not args.no_extras:
+        extras = run_extras(m, device, full=args.extras_full)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -372,6 +426,7 @@ def run_ours(args):
                     "images_per_s": round(e2e_val * 1e6 / n_points, 1),
                     "api": "HostFramePipeline.run_pinned (pinned host in/out, 3 streams, chunk=%d)" % pipe.chunk},
             "gpu_launches": launches_per_step * K,
+            "oracle_check": "frame %d of the timed output equals oracle.depth_to_point_cloud bit for bit" % (B // 2),
             "roofline": {"bound": "hbm", "kernel": "emit_fast_kernel", "achieved": round(achieved, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": (round(measured_traffic_per_frame() * B) if measured_traffic_per_frame() else None),
@@ -392,10 +447,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_extras(m, device):
-    """Other BASELINE.json configurations, device-resident, CUDA-event timed (not the headline)."""
+def run_extras(m, device, full=False):
+    """The other BASELINE.json configurations, device-resident, CUDA-event timed (not the headline).  Every
+    entry carries its algorithmic bytes (4 D + 3 N + 24 N_out per frame), ms and the fraction of
+    the measured copy bandwidth."""
     import torch
     out = {}
+    peak = measured_peak()[0]
 
     def timeit(fn, iters=10):
         for _ in range(3):
@@ -411,13 +469,15 @@ def run_extras(m, device):
 
     g = torch.Generator(device=device)
     g.manual_seed(5)
-    for name, (H, W, h, w, B, zr, dens) in {
-        "1080p_dav2_depth_518x924": (1080, 1920, 518, 924, 64, None, "high"),
+    variants = {
+        "1080p_dav2_depth_518x924 (every real request resizes, app.py:186-188)": (1080, 1920, 518, 924, 64, None, "high"),
         "1080p_dav2_depth_density_medium (what the reference UI runs)": (1080, 1920, 518, 924, 64, None, "medium"),
         "1080p_native_zrange_0.5_9.5": (1080, 1920, 1080, 1920, 64, (0.5, 9.5), "high"),
+        "1080p_native_zrange_density_medium": (1080, 1920, 1080, 1920, 64, (0.5, 9.5), "medium"),
         "4k_native": (2160, 3840, 2160, 3840, 16, None, "high"),
         "4k_native_zrange_0.5_9.5": (2160, 3840, 2160, 3840, 16, (0.5, 9.5), "high"),
-    }.items():
+    }
+    for name, (H, W, h, w, B, zr, dens) in variants.items():
         eng = m.FrameEngine(H, W, h, w, batch=B, device=device)
         cfg = eng.make_config(density=dens, z_range=zr)
         depth = torch.rand((B, h, w), generator=g, device=device) * 20
@@ -427,46 +487,50 @@ def run_extras(m, device):
         s = torch.cuda.current_stream(device)
 
         def step():
-            eng.enqueue_stats(cfg, depth, s)
-            eng.enqueue_emit(cfg, depth, bgr, xyz, rgb, cnt, None, s)
+            eng.enqueue_path(cfg, depth, bgr, xyz, rgb, cnt, None, s, graph=True)
         ms = timeit(step)
         kept = int(cnt.sum())
         n_frame = eng.points_per_frame(cfg)
         alg = B * (4 * h * w + 3 * n_frame) + 24 * kept   # 4 D + 3 N + 24 N_out per frame
         out[name] = {"ms_per_step": round(ms, 4), "frames": B, "mpoints_out_per_s": round(kept / ms / 1e3, 1),
                      "images_per_s": round(B / ms * 1e3, 1), "kept_fraction": round(kept / (B * n_frame), 4),
-                     "alg_gbs": round(alg / ms / 1e6, 1)}
+                     "alg_bytes": alg, "alg_gbs": round(alg / ms / 1e6, 1), "frac_of_measured_peak": round(alg / ms / 1e6 / peak, 4)}
         del eng, depth, bgr, xyz, rgb
         torch.cuda.empty_cache()
     # BASELINE configs[2] / [4]: 4K frame, depth-range mask, voxel-size sweep (voxel stage alone)
     from profiles.voxel_sweep import sweep
-    out["4k_zrange_voxel_sweep"] = sweep(iters=5, peak=measured_peak()[0])
-    # row f3: writer byte layouts on one 1080p cloud (kernels only)
-    from profiles.writers_bench import bench as writers_bench
-    out["writers_1080p"] = writers_bench()
-    # row f1: statistical outlier removal on the stage's own clouds
-    from profiles.sor_bench import bench as sor_bench
-    out["sor_k20"] = sor_bench()
-    # the drop-in call itself: NumPy in, NumPy out, one image (what backend/app.py:468 does per request)
-    import numpy as np
-    rng = np.random.default_rng(1)
-    lat = {}
-    for name, (H, W, h, w, dens) in {"480p_dav2_medium (UI default)": (480, 640, 518, 686, "medium"),
-                                     "1080p_dav2_high": (1080, 1920, 518, 924, "high"),
-                                     "1080p_native_high": (1080, 1920, 1080, 1920, "high"),
-                                     "4k_dav2_high": (2160, 3840, 518, 924, "high")}.items():
-        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
-        dep = (rng.random((h, w)) * 20).astype(np.float32)
-        for _ in range(3):
-            p, c = m.depth_to_point_cloud(img, dep, density=dens, device=device)
-        ts = []
-        for _ in range(10):
-            t0 = time.perf_counter()
-            p, c = m.depth_to_point_cloud(img, dep, density=dens, device=device)
-            ts.append(time.perf_counter() - t0)
-        ts.sort()
-        lat[name] = {"points": len(p), "median_ms": round(ts[5] * 1e3, 3), "mpoints_per_s": round(len(p) / ts[5] / 1e6, 1)}
-    out["single_call_latency_numpy_in_out"] = lat
+    sw = sweep(iters=5, peak=peak)
+    out["configs[4] 4k_zrange_voxel_sweep (voxel stage alone)"] = sw
+    # configs[2]: one 4K frame through statistics + masked emit + 5 mm voxel grid (smooth scene)
+    from profiles.voxel_sweep import config2
+    out["configs[2] 4k_zrange_voxel_5mm (whole call)"] = config2(peak=peak)
+    if full:
+        # row f3: writer byte layouts on one 1080p cloud (kernels only)
+        from profiles.writers_bench import bench as writers_bench
+        out["writers_1080p"] = writers_bench()
+        # row f1: statistical outlier removal on the stage's own clouds
+        from profiles.sor_bench import bench as sor_bench
+        out["sor_k20"] = sor_bench()
+        # the drop-in call itself: NumPy in, NumPy out, one image (what backend/app.py:468 does per request)
+        import numpy as np
+        rng = np.random.default_rng(1)
+        lat = {}
+        for name, (H, W, h, w, dens) in {"480p_dav2_medium (UI default)": (480, 640, 518, 686, "medium"),
+                                         "1080p_dav2_high": (1080, 1920, 518, 924, "high"),
+                                         "1080p_native_high": (1080, 1920, 1080, 1920, "high"),
+                                         "4k_dav2_high": (2160, 3840, 518, 924, "high")}.items():
+            img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+            dep = (rng.random((h, w)) * 20).astype(np.float32)
+            for _ in range(3):
+                p, c = m.depth_to_point_cloud(img, dep, density=dens, device=device)
+            ts = []
+            for _ in range(10):
+                t0 = time.perf_counter()
+                p, c = m.depth_to_point_cloud(img, dep, density=dens, device=device)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            lat[name] = {"points": len(p), "median_ms": round(ts[5] * 1e3, 3), "mpoints_per_s": round(len(p) / ts[5] / 1e6, 1)}
+        out["single_call_latency_numpy_in_out"] = lat
     return out
 
 

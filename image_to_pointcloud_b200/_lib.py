@@ -11,7 +11,7 @@ D2PC_ABI_VERSION = 1
 D2PC_OK = 0
 FRAME_PENDING, FRAME_READY, FRAME_NEEDS_FALLBACK = 0, 1, 2
 BRANCH_PCT, BRANCH_MINMAX, BRANCH_ZEROS = 0, 1, 2
-PATH_GRAPH, PATH_NO_OVERLAP, PATH_NO_L2_HINTS, PATH_STREAMS = 1, 2, 4, 8
+PATH_GRAPH, PATH_NO_OVERLAP, PATH_NO_L2_HINTS, PATH_ORDERED = 1, 2, 4, 8
 
 EXPORTS = [
     "d2pc_abi_version", "d2pc_error_string", "d2pc_last_cuda_error", "d2pc_workspace_bytes",

@@ -67,35 +67,6 @@ struct SchedParams {
 };
 
 constexpr int kPathMinBlocks = 6;
-constexpr uint32_t kSpinLimit = 1u << 19;   // x ~2 us: about a second
-
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// thread 0 spins until pred(value at p) holds; false: timed out (abort flag raised)
-template <typename Pred>
-__device__ __forceinline__ bool spin_until(const uint32_t *p, uint32_t *abort_flag, Pred pred) {
-  uint32_t spins = 0, ns = 128;
-  while (!pred(ld_relaxed_u32(p))) {
-    __nanosleep(ns);                 // back off: hundreds of CTAs may poll the same line
-    if (ns < 2048u) ns <<= 1;
-    if (++spins > kSpinLimit || ((spins & 15u) == 0u && ld_relaxed_u32(abort_flag))) {
-      atomicExch(abort_flag, 1u);
-      return false;
-    }
-  }
-  (void)ld_acquire_u32(p);
-  return true;
-}
-
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -132,7 +103,7 @@ __global__ void __launch_bounds__(kEmitThreads, kPathMinBlocks) path_kernel(KPar
     __syncthreads();
     if (!s_go) return;
     if (TRACE && tid == 0 && k == 0u) *trace_slot(kp, f, 2 + 2 * (int)br) = global_ns();
-    select_part(kp, f, (int)br, k, sp.K, reinterpret_cast<float *>(s_dyn), s_sel,
+    select_part(kp, f, (int)br, k, sp.K, reinterpret_cast<float *>(s_dyn), kSliceCap, s_sel,
                 [&](const uint32_t *p, auto pred) { return spin_until(p, abort_flag, pred); });
     if (TRACE) {
       __syncthreads();
@@ -251,7 +222,7 @@ size_t path_kernel_smem() {
 static int env_int(const char *name, int dflt, int lo, int hi);
 
 // sample (all frames) -> persistent kernel -> status, all on one stream
-int path_persistent(const PathArgs &a, cudaStream_t st) {
+int path_ordered(const PathArgs &a, cudaStream_t st) {
   const D2pcConfig &cfg = a.cfg;
   KParams kp = make_kparams(cfg, a.d_depth, a.d_workspace);
   kp.hints = (a.flags & D2PC_PATH_NO_L2_HINTS) ? 0 : (kHintScanKeep | kHintEmitDepthFirst | kHintStreamFirst);
@@ -437,7 +408,7 @@ extern "C" int d2pc_path_enqueue(D2pcPath *p, const D2pcConfig *cfg, const float
   {
     const KParams kp0 = make_kparams(a.cfg, a.d_depth, a.d_workspace);
     const EmitArgs ea0 = make_emit_args(a.cfg, a.d_bgr, a.d_xyz, a.d_rgb, a.d_count);
-    if (!(flags & D2PC_PATH_STREAMS) && path_kernel_supported(a.cfg, kp0, ea0)) return path_persistent(a, st);
+    if ((flags & D2PC_PATH_ORDERED) && path_kernel_supported(a.cfg, kp0, ea0)) return path_ordered(a, st);
   }
   if (!(flags & D2PC_PATH_GRAPH)) return path_body(p, a, st);
 

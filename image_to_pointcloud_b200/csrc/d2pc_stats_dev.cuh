@@ -357,6 +357,41 @@ __device__ __forceinline__ void select_bracket(const KParams &kp, int b, int br,
 }
 
 // ------------------------------------------------------------------------------------------
+// bounded waits between CTAs of one launch (index-ordered kernels: a CTA only waits for CTAs with a smaller
+// index, which were dispatched before it, or for the few peers of a cooperative selection right behind it)
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kSpinLimit = 1u << 19;   // x ~2 us: about a second
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// thread 0 spins until pred(value at p) holds; false: timed out (abort flag raised)
+template <typename Pred>
+__device__ __forceinline__ bool spin_until(const uint32_t *p, uint32_t *abort_flag, Pred pred) {
+  uint32_t spins = 0, ns = 128;
+  while (!pred(ld_relaxed_u32(p))) {
+    __nanosleep(ns);                 // back off: hundreds of CTAs may poll the same line
+    if (ns < 2048u) ns <<= 1;
+    if (++spins > kSpinLimit || ((spins & 15u) == 0u && ld_relaxed_u32(abort_flag))) {
+      atomicExch(abort_flag, 1u);
+      return false;
+    }
+  }
+  (void)ld_acquire_u32(p);
+  return true;
+}
+
+__device__ __forceinline__ uint32_t *sched_abort_flag(const KParams &kp) { return kp.sched + 32u * kSchedQueues; }
+
+// ------------------------------------------------------------------------------------------
 // The same selection, cooperatively: K CTAs of the persistent path kernel share one bracket.  Each takes a
 // slice of the bracket's queue, keeps it in shared memory, classifies it and adds the inside keys to the
 // frame's global bucket histogram (L2 atomics).  The CTA that finishes last resolves the wanted ranks and
@@ -366,7 +401,7 @@ __device__ __forceinline__ void select_bracket(const KParams &kp, int b, int br,
 // bracket of the frame to finish, writes the frame's parameters.  ~10 us per frame instead of ~100 us for one
 // CTA walking 62 000 queued values twice.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kSliceCap = 6144;  // floats of dynamic shared memory holding a slice (the emit tile's staging: 24.6 KB)
+constexpr uint32_t kSliceCap = 6144;  // floats of dynamic shared memory a slice may use (callers pass their capacity)
 
 struct SelPartSmall {
   uint32_t c[6];
@@ -392,11 +427,11 @@ __device__ __forceinline__ void select_finish(FrameState *fs, SelShared *sh, int
   }
 }
 
-// part k of K of bracket br of frame b.  s_slice: kSliceCap floats (also >= 2 << 11 words for the general
-// selection).  spin(ptr, pred) -> bool is the caller's bounded wait (false: abort).  Returns false on abort.
+// part k of K of bracket br of frame b.  s_slice: slice_cap floats of shared memory (>= 2 << 11 words, which the
+// general selection needs).  spin(ptr, pred) -> bool is the caller's bounded wait (false: abort).  Returns false on abort.
 template <typename Spin>
 __device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, uint32_t k, uint32_t K, float *s_slice,
-                                            SelPartSmall &ss, Spin spin) {
+                                            uint32_t slice_cap, SelPartSmall &ss, Spin spin) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   FrameState *fs = kp.state + b;
   SelShared *sh = kp.sel + b;
@@ -413,7 +448,7 @@ __device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, ui
   const int shift = fast_shift(span);
   const uint32_t chunk = (nq + K - 1u) / K;
   const uint32_t s_lo = min(nq, k * chunk), s_hi = min(nq, s_lo + chunk), m = s_hi - s_lo;
-  const bool cached = chunk <= kSliceCap;
+  const bool cached = chunk <= slice_cap;
   if (tid < 6) ss.c[tid] = 0u;
   __syncthreads();
   {  // phase A: classify the slice, histogram of the inside keys

@@ -163,7 +163,7 @@ typedef struct D2pcPath D2pcPath;
 #define D2PC_PATH_GRAPH 1
 #define D2PC_PATH_NO_OVERLAP 2
 #define D2PC_PATH_NO_L2_HINTS 4
-#define D2PC_PATH_STREAMS 8
+#define D2PC_PATH_ORDERED 8
 int d2pc_path_create(D2pcPath **path);
 void d2pc_path_destroy(D2pcPath *path);
 int d2pc_path_enqueue(D2pcPath *path, const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,

@@ -56,9 +56,9 @@ def main(kind="native", B=128, subs=None):
     print("two-phase             %.4f ms  frac %.3f" % (ms, alg / ms / 1e6 / PEAK), flush=True)
     combos = subs or [(0, 3), (0, 4), (0, 6), (0, 8), (0, 12)]
     for S, L in combos:
-        # S == 0: the persistent path kernel with lookahead L frames; S > 0: the stream pipeline
-        for name, kw in ((("persistent", dict()),) if S == 0 else
-                         (("graph", dict(graph=True, flags=_lib.PATH_STREAMS)), ("nograph", dict(graph=False, flags=_lib.PATH_STREAMS)))):
+        # S == 0: the index-ordered path kernel with lookahead L frames; S > 0: the stream pipeline
+        for name, kw in ((("ordered", dict(flags=_lib.PATH_ORDERED)),) if S == 0 else
+                         (("graph", dict(graph=True)), ("nograph", dict(graph=False)))):
             if name == "nograph" and os.environ.get("SWEEP_NOGRAPH", "0") != "1":
                 continue
             xyz.zero_(); rgb.zero_()

@@ -23,7 +23,7 @@ def main(B=32, D=6, H=1080, W=1920):
     cnt = torch.zeros(B, dtype=torch.int32, device=dev)
     s = torch.cuda.current_stream(dev)
     for _ in range(3):
-        eng.enqueue_path(cfg, depth, bgr, xyz, rgb, cnt, None, s, lookahead=D)
+        eng.enqueue_path(cfg, depth, bgr, xyz, rgb, cnt, None, s, lookahead=D, flags=8)
     torch.cuda.synchronize()
     # locate the scheduler words: the workspace layout ends [.. taps | sched | resized]; native depth: sched is last
     ws = eng.workspace.cpu().numpy()

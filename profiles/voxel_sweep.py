@@ -66,6 +66,48 @@ def sweep(H=2160, W=3840, iters=5, peak=None):
     return out
 
 
+def config2(H=2160, W=3840, voxel=0.005, iters=5, peak=None):
+    """BASELINE configs[2]: ONE 4K frame (smooth scene), statistics + z-range-masked emit + 5 mm voxel grid,
+    device-resident, CUDA-event timed; algorithmic bytes 4 D + 3 N + 24 M (emit) + 24 M + 24 V (voxel stage)."""
+    dev = torch.device("cuda", 0)
+    maps, g = depth_maps(dev, H, W)
+    depth = maps["scene"]
+    bgr = torch.randint(0, 256, (1, H, W, 3), generator=g, device=dev, dtype=torch.uint8)
+    eng = m.FrameEngine(H, W, batch=1, device=dev)
+    cfg = eng.make_config(density="high", z_range=(0.5, 9.5), want_bounds=True)
+    xyz, rgb = eng.alloc_outputs(cfg)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    bounds = torch.empty((1, 6), dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream(dev)
+    res = EmitResult(xyz, rgb, cnt, bounds)
+
+    def stage():
+        eng.enqueue_path(cfg, depth, bgr, xyz, rgb, cnt, bounds, s)
+
+    def whole():
+        stage()
+        return eng.voxel_downsample(cfg, res, voxel, check_error=False)
+    out = {}
+    for name, fn in (("stage_ms", stage), ("whole_ms", whole)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = round(a.elapsed_time(b) / iters, 4)
+    M, V = int(cnt[0]), int(r[3][0])
+    alg = 4 * H * W + 3 * H * W + 24 * M + 24 * M + 24 * V
+    out.update({"points_in": H * W, "kept": M, "voxels": V, "voxel_size": voxel, "alg_bytes": alg,
+                "alg_gbs": round(alg / out["whole_ms"] / 1e6, 1)})
+    if peak:
+        out["frac_of_measured_peak"] = round(alg / out["whole_ms"] / 1e6 / peak, 4)
+    return out
+
+
 if __name__ == "__main__":
     it = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     peak = None
