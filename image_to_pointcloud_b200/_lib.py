@@ -61,9 +61,16 @@ def load_library(path: str | None = None) -> C.CDLL:
     if path is None:
         try:
             p = build_library()
-        except Exception:
+        except Exception as e:
+            # No compiler on this box (or the build failed).  A library built from exactly these sources is
+            # fine; a stale one is not: tests and benchmarks would silently report against old kernels.
+            from .build import source_digest, stored_digest
             if not os.path.exists(LIB_PATH):
                 raise
+            have, want = stored_digest(), source_digest()
+            if have != want:
+                raise RuntimeError(f"libd2pc.so is stale (built from sources {have}, tree is {want}) and could not "
+                                   f"be rebuilt: {e}") from e
             p = LIB_PATH
     lib = C.CDLL(p)
     vp = C.c_void_p

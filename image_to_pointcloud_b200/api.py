@@ -14,31 +14,46 @@ All arithmetic runs in the sm_100a kernels of libd2pc.so.  There is no CPU path 
 from __future__ import annotations
 
 import logging
+import threading
 from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
-from .engine import DENSITY_STEP, EmitResult, FrameEngine
+from .engine import DENSITY_STEP, MAX_SMOOTH_KSIZE, EmitResult, FrameEngine, smoothing_kernel
 
 logger = logging.getLogger(__name__)
 
+# One engine (workspace + pinned / device staging buffers) per geometry and device, shared by all callers.
+# Threading contract: the cache is guarded by _CACHE_LOCK, and every engine carries its own lock that is held
+# from staging the inputs until the results have left the device, so concurrent calls (a thread pool,
+# ``run_in_executor``) on the same geometry serialise instead of overwriting each other's staged frame; calls
+# on different geometries or devices run concurrently.
 _ENGINES: Dict[tuple, "FrameEngine"] = {}
 _STAGING: Dict[tuple, dict] = {}
+_CACHE_LOCK = threading.Lock()
 
 
 def _engine_for(img_h, img_w, img_c, dep_h, dep_w, device) -> FrameEngine:
     dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     key = (str(dev), img_h, img_w, img_c, dep_h, dep_w)
+    with _CACHE_LOCK:
+        return _engine_locked(key, dev, img_h, img_w, img_c, dep_h, dep_w)
+
+
+def _engine_locked(key, dev, img_h, img_w, img_c, dep_h, dep_w) -> FrameEngine:
     eng = _ENGINES.get(key)
     if eng is None:
         if len(_ENGINES) > 8:  # geometry changes per upload in the web app; keep the cache small
+            # engines still in use by another thread stay alive through that thread's reference
             _ENGINES.clear()
             _STAGING.clear()
         eng = FrameEngine(img_h, img_w, dep_h, dep_w, batch=1, img_c=img_c, device=dev)
+        eng._staging = None
         _ENGINES[key] = eng
         with torch.cuda.device(dev):
-            _STAGING[key] = dict(
+            eng._staging = _STAGING[key] = dict(
+                lock=threading.Lock(),
                 depth_pin=torch.empty((1, dep_h, dep_w), dtype=torch.float32, pin_memory=True),
                 depth_dev=torch.empty((1, dep_h, dep_w), dtype=torch.float32, device=dev),
                 bgr_pin=(torch.empty((1, img_h, img_w, img_c), dtype=torch.uint8, pin_memory=True)
@@ -82,8 +97,14 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
                          voxel_size: Optional[float] = None,
                          return_voxel_index: bool = False,
                          return_bounds: bool = False,
+                         pinned: bool = True,
                          device=None) -> tuple:
-    """Convert a depth map to a coloured 3-D point cloud on a B200 (see module docstring)."""
+    """Convert a depth map to a coloured 3-D point cloud on a B200 (see module docstring).
+
+    ``pinned=True`` (default) returns arrays backed by page-locked host memory (the device -> host copy runs at
+    PCIe speed and the call returns as soon as it lands); a caller that keeps many results alive (the reference
+    keeps each job's arrays, app.py:540-559) can pass ``pinned=False`` to get ordinary pageable arrays instead.
+    Thread-safe: calls on the same geometry serialise on the engine's lock."""
     try:
         if not isinstance(image, np.ndarray) or not isinstance(depth, np.ndarray):
             raise TypeError("image and depth must be numpy arrays")
@@ -93,59 +114,75 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
         if image.dtype != np.uint8:
             raise TypeError("image must be uint8 (cv2.imdecode output)")
         check_depth_dtype(depth, int(img_h), int(img_w))
+        if smooth and len(smoothing_kernel(smooth_ksize)) > MAX_SMOOTH_KSIZE:
+            # the reference accepts any size (cv2.GaussianBlur); this build keeps the coefficients in kernel
+            # arguments and stops at 31 -- refused before any GPU work (the reference's only caller uses 5)
+            raise ValueError(f"smooth_ksize {smooth_ksize} gives a kernel larger than {MAX_SMOOTH_KSIZE}")
         img_c = _image_channels(image)
         eng = _engine_for(int(img_h), int(img_w), img_c, int(dep_h), int(dep_w), device)
-        st = _STAGING[(str(eng.device), int(img_h), int(img_w), img_c, int(dep_h), int(dep_w))]
-        want_voxel = voxel_size is not None
-        cfg = eng.make_config(density=density, invert=invert, depth_scale=float(depth_scale), fov=fov,
-                              z_range=z_range, drop_nonfinite=drop_nonfinite,
-                              want_bounds=(want_voxel or return_bounds))
-        stream = torch.cuda.current_stream(eng.device)
-        with torch.cuda.device(eng.device):
-            # host -> pinned staging -> device (d = depth.astype(np.float32), app.py:191)
-            st["depth_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(depth, dtype=np.float32).reshape(dep_h, dep_w)))
-            st["depth_dev"].copy_(st["depth_pin"], non_blocking=True)
-            if img_c >= 3:
-                st["bgr_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(image)))
-                st["bgr_dev"].copy_(st["bgr_pin"], non_blocking=True)
-            # Without a mask every grid point is emitted: the row count is known, so the device -> host copies
-            # are enqueued behind the emit and the call synchronises once.
-            plain = z_range is None and not drop_nonfinite and not want_voxel
-            host = {}
-
-            def copy_out(xyz, rgb, count, bounds):
-                for key, t in (("xyz", xyz), ("rgb", rgb)):
-                    if key not in host:
-                        host[key] = torch.empty(t.shape[1:], dtype=t.dtype, pin_memory=True)
-                    host[key].copy_(t[0], non_blocking=True)
-                if bounds is not None:
-                    if "bounds" not in host:
-                        host["bounds"] = torch.empty((6,), dtype=torch.float32, pin_memory=True)
-                    host["bounds"].copy_(bounds[0], non_blocking=True)
-
-            res = eng.process(cfg, st["depth_dev"], st["bgr_dev"], stream=stream,
-                              smooth_ksize=(smooth_ksize if smooth else None), after_emit=copy_out if plain else None)
-            if plain:   # process() has synchronised the stream
-                out = (host["xyz"].numpy(), host["rgb"].numpy())
-                if return_bounds:
-                    out = out + (bounds_dict(host["bounds"].numpy()),)
-                return out
-            if want_voxel:
-                vxyz, vrgb, vidx, vcount = eng.voxel_downsample(cfg, res, float(voxel_size),
-                                                                want_index=return_voxel_index, stream=stream)
-                n = int(vcount.cpu()[0])
-                out = (_to_host(vxyz[0, :n]), _to_host(vrgb[0, :n]))
-                if return_voxel_index:
-                    out = out + (vidx[0, :n].cpu().numpy(),)
-                return out
-            n = int(res.count.cpu()[0])
-            out = (_to_host(res.xyz[0, :n]), _to_host(res.rgb[0, :n]))
-            if return_bounds:
-                out = out + (bounds_dict(res.bounds[0].cpu().numpy()),)
-            return out
+        st = eng._staging
+        with st["lock"]:
+            return _run_locked(eng, st, image, depth, img_c, dep_h, dep_w, density, invert, depth_scale, smooth,
+                               smooth_ksize, fov, z_range, drop_nonfinite, voxel_size, return_voxel_index,
+                               return_bounds, pinned)
     except Exception as e:  # same convention as the reference (app.py:248-250): log and re-raise
         logger.error(f"Error in point cloud generation: {str(e)}")
         raise
+
+
+def _unpin(a: np.ndarray, pinned: bool) -> np.ndarray:
+    return a if pinned else np.array(a, copy=True)
+
+
+def _run_locked(eng, st, image, depth, img_c, dep_h, dep_w, density, invert, depth_scale, smooth, smooth_ksize, fov,
+                z_range, drop_nonfinite, voxel_size, return_voxel_index, return_bounds, pinned):
+    want_voxel = voxel_size is not None
+    cfg = eng.make_config(density=density, invert=invert, depth_scale=float(depth_scale), fov=fov,
+                          z_range=z_range, drop_nonfinite=drop_nonfinite,
+                          want_bounds=(want_voxel or return_bounds))
+    stream = torch.cuda.current_stream(eng.device)
+    with torch.cuda.device(eng.device):
+        # host -> pinned staging -> device (d = depth.astype(np.float32), app.py:191)
+        st["depth_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(depth, dtype=np.float32).reshape(dep_h, dep_w)))
+        st["depth_dev"].copy_(st["depth_pin"], non_blocking=True)
+        if img_c >= 3:
+            st["bgr_pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(image)))
+            st["bgr_dev"].copy_(st["bgr_pin"], non_blocking=True)
+        # Without a mask every grid point is emitted: the row count is known, so the device -> host copies
+        # are enqueued behind the emit and the call synchronises once.
+        plain = z_range is None and not drop_nonfinite and not want_voxel
+        host = {}
+
+        def copy_out(xyz, rgb, count, bounds):
+            for key, t in (("xyz", xyz), ("rgb", rgb)):
+                if key not in host:
+                    host[key] = torch.empty(t.shape[1:], dtype=t.dtype, pin_memory=True)
+                host[key].copy_(t[0], non_blocking=True)
+            if bounds is not None:
+                if "bounds" not in host:
+                    host["bounds"] = torch.empty((6,), dtype=torch.float32, pin_memory=True)
+                host["bounds"].copy_(bounds[0], non_blocking=True)
+
+        res = eng.process(cfg, st["depth_dev"], st["bgr_dev"], stream=stream,
+                          smooth_ksize=(smooth_ksize if smooth else None), after_emit=copy_out if plain else None)
+        if plain:   # process() has synchronised the stream
+            out = (_unpin(host["xyz"].numpy(), pinned), _unpin(host["rgb"].numpy(), pinned))
+            if return_bounds:
+                out = out + (bounds_dict(host["bounds"].numpy()),)
+            return out
+        if want_voxel:
+            vxyz, vrgb, vidx, vcount = eng.voxel_downsample(cfg, res, float(voxel_size),
+                                                            want_index=return_voxel_index, stream=stream)
+            n = int(vcount.cpu()[0])
+            out = (_unpin(_to_host(vxyz[0, :n]), pinned), _unpin(_to_host(vrgb[0, :n]), pinned))
+            if return_voxel_index:
+                out = out + (vidx[0, :n].cpu().numpy(),)
+            return out
+        n = int(res.count.cpu()[0])
+        out = (_unpin(_to_host(res.xyz[0, :n]), pinned), _unpin(_to_host(res.rgb[0, :n]), pinned))
+        if return_bounds:
+            out = out + (bounds_dict(res.bounds[0].cpu().numpy()),)
+        return out
 
 
 DEPTH_PREVIEW_MAX = 2048  # reference backend/app.py:44
@@ -157,7 +194,7 @@ def depth_preview_bgr(depth: np.ndarray, invert: bool = True, device=None) -> np
     d = np.ascontiguousarray(depth, dtype=np.float32)
     h, w = d.shape[:2]
     eng = _engine_for(int(h), int(w), 1, int(h), int(w), device)
-    with torch.cuda.device(eng.device):
+    with eng._staging["lock"], torch.cuda.device(eng.device):
         dev = torch.from_numpy(d.reshape(1, h, w)).to(eng.device)
         return eng.depth_preview(dev, invert=invert)[0].cpu().numpy()
 

@@ -41,6 +41,14 @@ def source_digest() -> str:
     return h.hexdigest()
 
 
+def stored_digest() -> str:
+    """Digest of the sources the in-tree library was built from ("" if unknown)."""
+    try:
+        return open(os.path.join(BUILD_DIR, "libd2pc.sha256")).read().strip()
+    except OSError:
+        return ""
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD_DIR, exist_ok=True)
     stamp = os.path.join(BUILD_DIR, "libd2pc.sha256")

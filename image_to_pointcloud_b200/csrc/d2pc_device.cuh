@@ -243,6 +243,7 @@ struct EmitArgs {
   PixelConsts pc;
   int32_t use_z, drop_nf, want_bounds;
   float z_min, z_max;
+  uint32_t frame0;   // output slot of the parameter block's frame 0 (sub-batch slices keep xyz / rgb unsliced)
 };
 
 int validate_config(const D2pcConfig *cfg);   // d2pc_api.cu

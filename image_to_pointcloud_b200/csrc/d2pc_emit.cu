@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_generic_kernel(KParams kp, 
     if (tile == 0 && tid == 0) ea.count[b] = g.N;
   }
 
-  const size_t g0 = ((size_t)b * g.N + dest_row) * 3;
+  const size_t g0 = ((size_t)((uint32_t)b + ea.frame0) * g.N + dest_row) * 3;
   const uint32_t s_off = (uint32_t)(g0 & 3);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -354,6 +354,7 @@ EmitArgs make_emit_args(const D2pcConfig &cfg, const uint8_t *d_bgr, float *d_xy
   ea.pc.inv_f = 1.0 / cfg.f; ea.pc.invert = cfg.invert;
   ea.use_z = cfg.use_z_range; ea.drop_nf = cfg.drop_nonfinite; ea.want_bounds = cfg.want_bounds;
   ea.z_min = cfg.z_min; ea.z_max = cfg.z_max;
+  ea.frame0 = 0;
   return ea;
 }
 
@@ -361,8 +362,7 @@ EmitArgs make_emit_args(const D2pcConfig &cfg, const uint8_t *d_bgr, float *d_xy
 EmitArgs slice_emit_args(const EmitArgs &ea, const Geom &g, int b0) {
   EmitArgs s = ea;
   if (ea.bgr) s.bgr = ea.bgr + (size_t)b0 * g.P * (size_t)g.C;
-  s.xyz = ea.xyz + (size_t)b0 * g.N * 3;
-  s.rgb = ea.rgb + (size_t)b0 * g.N * 3;
+  s.frame0 = ea.frame0 + (uint32_t)b0;  // xyz / rgb keep their 16-byte aligned base: rows are addressed through frame0
   s.count = ea.count + b0;
   return s;
 }

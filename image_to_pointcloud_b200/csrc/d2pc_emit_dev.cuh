@@ -290,7 +290,7 @@ __device__ __forceinline__ bool emit_fast_tile(const KParams &kp, const EmitArgs
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged rows visible to the async proxy
     __syncthreads();
     const uint32_t rows = min((uint32_t)kEmitTile, P - tile_base);
-    const size_t g0 = ((size_t)b * kp.g.N + tile_base) * 3;
+    const size_t g0 = ((size_t)(b + ea.frame0) * kp.g.N + tile_base) * 3;
     if (tid == 0) {
       const uint32_t bytes = rows * 12u;  // rows % 4 == 0 here
       const uint32_t sx = (uint32_t)__cvta_generic_to_shared(s_xyz), sr = (uint32_t)__cvta_generic_to_shared(s_rgb);
@@ -322,7 +322,7 @@ __device__ __forceinline__ bool emit_fast_tile(const KParams &kp, const EmitArgs
     // destination row: exclusive prefix of the kept counts, computed before this launch by
     // mask_count_kernel + mask_offsets_kernel (no inter-CTA dependency inside emit)
     const uint32_t dest_row = (uint32_t)(kp.tile_state[(size_t)b * kp.emit_tiles + tile] >> 32);
-    const size_t g0 = ((size_t)b * kp.g.N + dest_row) * 3;
+    const size_t g0 = ((size_t)(b + ea.frame0) * kp.g.N + dest_row) * 3;
     const uint32_t s_off = (uint32_t)(g0 & 3);
     const float col[12] = {
         byte_to_float(c0, D2PC_B2), byte_to_float(c0, D2PC_B1), byte_to_float(c0, D2PC_B0),
