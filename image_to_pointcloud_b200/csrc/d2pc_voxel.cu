@@ -4,47 +4,48 @@
 //   vmin = min_xyz - 0.5*vs ;  idx = floor((p - vmin) / vs) per axis ;
 //   one output row per occupied voxel = arithmetic mean of member points and colours.
 //
-// Memory plan.  One open-addressing hash table per engine, 64-byte entries (two 32 B sectors) so
-// that a point touches one line of the table:
-//   [ key u64 | count<<32 + sum r | sum g<<32 + sum b | sum x | sum y | sum z | pad 16 ]
+// Memory plan ("representative point" scheme).  What must be looked up at random is kept small enough to live in
+// the 126 MB L2; everything large is touched in streaming order:
+//   table  u32[2 N]   open addressing, one 4-byte entry per slot = 8-bit fingerprint | 24-bit row index of the
+//                     voxel's REPRESENTATIVE row (the row that claimed the slot).  66 MB for a 4K frame.
+//   keys   u64[N]     packed voxel index of each run leader (written in row order; read back at random only when a
+//                     fingerprint matches, i.e. practically only for true members of the voxel)
+//   acc    u64[5 N]   per ROW accumulators [count<<32 + sum r | sum g<<32 + sum b | sum x | sum y | sum z].  A run
+//                     leader first stores its own (run-merged) sums at acc[row] in row order, fences, and only then
+//                     tries to claim the slot; rows that find their voxel already claimed add their sums to the
+//                     representative's accumulators with 5 RED.64.  No accumulator is ever zeroed or swept.
+//   flags  u8[N]      1 = this row is a representative
 //   * colours are the integral 0..255 floats emit writes: their sums are exact integers, two packed
 //     64-bit adds carry count, r, g and b (N < 2^24 rows keeps every 32-bit field from overflowing);
 //   * coordinates are accumulated as 64-bit fixed point of (p - vmin) with a power-of-two scale
 //     chosen per frame so that N * extent * scale < 2^62: integer adds are associative, so the
 //     means are deterministic (run-to-run identical) and within 2^-38 * extent of the float64 sums.
-//   * insert: 4 consecutive rows per thread, equal neighbouring keys are merged in registers first
-//     (raster neighbours share voxels in smooth scenes); one probe (load, CAS only on an empty
-//     slot) + 5 RED.64 per run.  Slots claimed by a CTA are queued in shared memory and appended
-//     to the frame's occupied-slot list with one global atomic per CTA.
-//   * extract: one thread per occupied slot: mean, AoS rows, clear the entry.  The table is never
-//     swept: cost scales with the voxels, not with the capacity, and the table stays clean.
+//   * insert: one row per lane; rows that share a voxel with their left neighbour form a run that is summed in
+//     registers by a segmented warp scan (raster neighbours share voxels in smooth scenes); the run's last lane
+//     probes.  A read-only probe comes first, so members of an existing voxel never write their own slot.
+//   * extract: streams over the rows; representatives turn their accumulators into means and are compacted
+//     (CTA scan + one atomic per CTA; the order of the output rows is unspecified, as in Open3D).
+// Against the first design (64-byte hash entries, 1 GB table for a 4K frame, every access a random DRAM
+// read-modify-write) the random traffic drops to 4-byte entries in an L2-resident table.
 #include "d2pc_device.cuh"
 
 namespace d2pc {
 
-constexpr unsigned long long kVoxEmpty = 0xFFFFFFFFFFFFFFFFull;
-constexpr unsigned long long kVoxMagic = 0x64327063766f7832ull;  // "d2pcvox2"
+constexpr unsigned long long kVoxNoKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kVoxEmptySlot = 0xFFFFFFFFu;
+constexpr unsigned long long kVoxMagic = 0x64327063766f7833ull;  // "d2pcvox3"
 constexpr int kVoxBits = 21;
 constexpr int kVoxThreads = 256;
 constexpr int kVoxPerThread = 4;
 constexpr int kVoxTile = kVoxThreads * kVoxPerThread;
-constexpr uint32_t kVoxMaxRows = 1u << 24;  // 32-bit packed count / colour fields
-
-struct __align__(64) VoxEntry {
-  unsigned long long key;
-  unsigned long long cnt_r;   // count << 32 | sum of r
-  unsigned long long g_b;     // sum of g << 32 | sum of b
-  unsigned long long sx, sy, sz;  // fixed-point sums of (p - vmin) * scale
-  unsigned long long pad[2];
-};
-static_assert(sizeof(VoxEntry) == 64, "entry must be one 64-byte line");
+constexpr uint32_t kVoxMaxRows = 1u << 24;  // 24-bit row index in a slot; 32-bit packed count / colour fields
 
 struct __align__(256) VoxHeader {
   unsigned long long magic;  // kVoxMagic once d2pc_voxel_table_init has run
-  uint32_t cap;              // entries (power of two)
-  uint32_t n_list;           // occupied slots of the frame being processed
-  uint32_t done;             // extract CTAs finished (ticket for the reset)
-  uint32_t frame_cap;        // capacity used for the current frame (pow2 >= 2 * rows, <= cap)
+  uint32_t cap;              // slots allocated
+  uint32_t n_out;            // output rows of the frame being processed
+  uint32_t done;             // extract CTAs finished (ticket for the final count)
+  uint32_t frame_cap;        // slots used for the current frame (2 * rows, >= 1024, <= cap)
   double vmin[3];
   double scale;              // fixed-point scale (power of two)
   int32_t bad;               // table was not initialised
@@ -52,57 +53,58 @@ struct __align__(256) VoxHeader {
 
 struct VoxTable {
   VoxHeader *hdr;
-  VoxEntry *ent;    // [cap]
-  uint32_t *list;   // [n_rows]
-  uint32_t cap;
+  uint32_t *slots;               // [cap]
+  unsigned long long *keys;      // [rows]
+  unsigned long long *acc;       // [rows][5]
+  uint8_t *flags;                // [rows]
+  uint32_t cap, rows;
 };
 
 inline uint32_t vox_capacity(uint32_t n_rows) {
-  uint32_t c = 1024;
-  while (c < 2u * n_rows && c < 0x80000000u) c <<= 1;
-  return c;
+  const unsigned long long c = 2ull * n_rows;
+  return (uint32_t)(c < 1024ull ? 1024ull : c);
 }
 inline size_t vox_bytes(uint32_t cap, uint32_t n_rows) {
-  return sizeof(VoxHeader) + (size_t)cap * sizeof(VoxEntry) + align_up((size_t)n_rows * 4, 256);
+  return sizeof(VoxHeader) + align_up((size_t)cap * 4, 256) + align_up((size_t)n_rows * 8, 256) +
+         align_up((size_t)n_rows * 40, 256) + align_up((size_t)n_rows, 256);
 }
-inline VoxTable vox_table(void *base, uint32_t cap) {
+inline VoxTable vox_table(void *base, uint32_t cap, uint32_t n_rows) {
   VoxTable t;
   char *p = (char *)base;
-  t.hdr = (VoxHeader *)p;  p += sizeof(VoxHeader);
-  t.ent = (VoxEntry *)p;   p += (size_t)cap * sizeof(VoxEntry);
-  t.list = (uint32_t *)p;
+  t.hdr = (VoxHeader *)p;              p += sizeof(VoxHeader);
+  t.slots = (uint32_t *)p;             p += align_up((size_t)cap * 4, 256);
+  t.keys = (unsigned long long *)p;    p += align_up((size_t)n_rows * 8, 256);
+  t.acc = (unsigned long long *)p;     p += align_up((size_t)n_rows * 40, 256);
+  t.flags = (uint8_t *)p;
   t.cap = cap;
+  t.rows = n_rows;
   return t;
 }
 
-__device__ __forceinline__ uint32_t hash_u64(unsigned long long k) {
+__device__ __forceinline__ unsigned long long hash_u64(unsigned long long k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-  return (uint32_t)k;
+  return k;
 }
 
 __global__ void vox_init_kernel(VoxTable t) {
-  const size_t n16 = (size_t)t.cap * (sizeof(VoxEntry) / 16);
-  uint4 *p = reinterpret_cast<uint4 *>(t.ent);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-    // 16-byte word 0 of an entry holds the key: all ones = empty; everything else zero
-    p[i] = ((i & 3) == 0) ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     t.hdr->magic = kVoxMagic;
     t.hdr->cap = t.cap;
-    t.hdr->n_list = 0;
+    t.hdr->n_out = 0;
     t.hdr->done = 0;
     t.hdr->bad = 0;
   }
 }
 
-// per frame: origin, fixed-point scale, capacity used for this frame
+// per frame: origin, fixed-point scale, slots used for this frame
 __global__ void vox_begin_kernel(VoxTable t, const uint32_t *count, const float *bounds, double vs, uint32_t *ocount,
                                  int32_t *err) {
   if (threadIdx.x != 0) return;
   VoxHeader *h = t.hdr;
   *ocount = 0;
-  if (h->magic != kVoxMagic || h->cap != t.cap) { h->bad = 1; *err = 2; return; }
+  h->n_out = 0;
+  h->done = 0;
+  if (h->magic != kVoxMagic || h->cap != t.cap) { h->bad = 1; h->frame_cap = 0; *err = 2; return; }
   *err = 0;
   h->bad = 0;
   const double half = vs * 0.5;
@@ -117,9 +119,18 @@ __global__ void vox_begin_kernel(VoxTable t, const uint32_t *count, const float 
   int ex = 0;
   if (ext > 0.0 && ext < 1.0e300) frexp(ext, &ex);  // ext = m * 2^ex, 0.5 <= m < 1
   h->scale = ldexp(1.0, 38 - ex);
-  uint32_t m = *count, c = 1024;
-  while (c < 2u * m && c < t.cap) c <<= 1;
-  h->frame_cap = c;
+  const unsigned long long m2 = 2ull * (unsigned long long)*count;
+  h->frame_cap = (uint32_t)(m2 < 1024ull ? 1024ull : (m2 > t.cap ? t.cap : m2));
+}
+
+// empty slots and clear flags for the rows of this frame (the sizes come from the header: no host sync)
+__global__ void __launch_bounds__(256) vox_clear_kernel(VoxTable t, const uint32_t *count) {
+  const uint32_t cap4 = (t.hdr->frame_cap + 3u) / 4u, fl16 = (*count + 15u) / 16u;
+  uint4 *s4 = reinterpret_cast<uint4 *>(t.slots), *f4 = reinterpret_cast<uint4 *>(t.flags);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap4; i += stride)
+    s4[i] = make_uint4(kVoxEmptySlot, kVoxEmptySlot, kVoxEmptySlot, kVoxEmptySlot);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fl16; i += stride) f4[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 struct VoxRun {
@@ -127,28 +138,86 @@ struct VoxRun {
   unsigned long long cnt_r, g_b, sx, sy, sz;
 };
 
-__device__ __forceinline__ void vox_flush(const VoxTable &t, uint32_t mask, const VoxRun &r, uint32_t *s_new,
-                                          uint32_t *s_nnew) {
-  uint32_t slot = hash_u64(r.key) & mask;
+__device__ __forceinline__ uint32_t ld_slot(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_key(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void vox_publish(const VoxTable &t, const VoxRun &r, uint32_t row) {
+  unsigned long long *a = t.acc + 5 * (size_t)row;
+  a[0] = r.cnt_r; a[1] = r.g_b; a[2] = r.sx; a[3] = r.sy; a[4] = r.sz;
+  t.keys[row] = r.key;
+}
+__device__ __forceinline__ void vox_add(const VoxTable &t, const VoxRun &r, uint32_t rep) {
+  unsigned long long *a = t.acc + 5 * (size_t)rep;
+  atomicAdd(a + 0, r.cnt_r);
+  atomicAdd(a + 1, r.g_b);
+  atomicAdd(a + 2, r.sx);
+  atomicAdd(a + 3, r.sy);
+  atomicAdd(a + 4, r.sz);
+}
+
+// The run leaders a lane holds (NR rows, `act` = this one leads a run; their sums and keys are already published
+// and fenced): claim each voxel's slot or add the run's sums to the representative that holds it.  The NR probe
+// chains are interleaved (claims together, key reads of fingerprint matches together), so a lane has NR
+// independent L2 round trips in flight.
+template <int NR>
+__device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap, const unsigned long long (&key)[NR],
+                                          const uint32_t (&row)[NR], const bool (&act)[NR]) {
+  uint32_t slot[NR], fp[NR], e[NR];
+  bool todo[NR];
+#pragma unroll
+  for (int h = 0; h < NR; ++h) {
+    const unsigned long long hh = hash_u64(key[h]);
+    fp[h] = (uint32_t)(hh & 0xFFu) << 24;
+    slot[h] = (uint32_t)(((hh >> 32) * (unsigned long long)frame_cap) >> 32);
+    todo[h] = act[h];
+  }
   while (true) {
-    VoxEntry *e = t.ent + slot;
-    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&e->key);
-    if (k == kVoxEmpty) {
-      k = atomicCAS(&e->key, kVoxEmpty, r.key);
-      if (k == kVoxEmpty) {  // this thread claimed the slot: queue it for the occupied list
-        s_new[atomicAdd(s_nnew, 1u)] = slot;
-        break;
+    bool any = false;
+#pragma unroll
+    for (int h = 0; h < NR; ++h) any = any || todo[h];
+    if (!any) break;
+#pragma unroll
+    for (int h = 0; h < NR; ++h)
+      if (todo[h]) e[h] = atomicCAS(t.slots + slot[h], kVoxEmptySlot, fp[h] | row[h]);
+    unsigned long long k[NR];
+    bool cmp[NR];
+#pragma unroll
+    for (int h = 0; h < NR; ++h) {
+      cmp[h] = false;
+      if (!todo[h]) continue;
+      if (e[h] == kVoxEmptySlot) {  // the claim succeeded: this row represents the voxel
+        t.flags[row[h]] = 1;
+        todo[h] = false;
+      } else if ((e[h] & 0xFF000000u) == fp[h]) {
+        cmp[h] = true;
+        k[h] = ld_key(t.keys + (e[h] & 0x00FFFFFFu));
       }
     }
-    if (k == r.key) break;
-    slot = (slot + 1) & mask;
+#pragma unroll
+    for (int h = 0; h < NR; ++h) {
+      if (!todo[h]) continue;
+      if (cmp[h] && k[h] == key[h]) {  // a member of that row's voxel: its own published sums go to the representative
+        const unsigned long long *mine = t.acc + 5 * (size_t)row[h];
+        unsigned long long *a = t.acc + 5 * (size_t)(e[h] & 0x00FFFFFFu);
+        unsigned long long v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) v[c] = __ldcg(mine + c);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) atomicAdd(a + c, v[c]);
+        todo[h] = false;
+      } else {
+        slot[h] = slot[h] + 1u == frame_cap ? 0u : slot[h] + 1u;
+      }
+    }
   }
-  VoxEntry *e = t.ent + slot;
-  atomicAdd(&e->cnt_r, r.cnt_r);
-  atomicAdd(&e->g_b, r.g_b);
-  atomicAdd(&e->sx, r.sx);
-  atomicAdd(&e->sy, r.sy);
-  atomicAdd(&e->sz, r.sz);
 }
 
 __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int d) {
@@ -157,53 +226,40 @@ __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, 
 
 // One row per lane, kVoxPerThread consecutive 32-row groups per warp.  Rows of a group that share a
 // voxel with their left neighbour form a run; a segmented warp scan sums each run into its last
-// lane, which alone touches the table (raster neighbours share voxels whenever the voxel is larger
-// than the pixel footprint).  Every lane has one independent probe in flight.
+// lane, which alone touches the table.  Every lane has one independent probe in flight.
 __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, const float *xyz, const float *rgb,
                                                                     const uint32_t *count, double vs, int32_t *err) {
-  __shared__ uint32_t s_new[kVoxTile];
-  __shared__ uint32_t s_nnew, s_base;
   const uint32_t M = *count;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kVoxTile;
   if (tile_base >= M || t.hdr->bad) return;
-  if (threadIdx.x == 0) s_nnew = 0;
-  __syncthreads();
   const double vmin0 = t.hdr->vmin[0], vmin1 = t.hdr->vmin[1], vmin2 = t.hdr->vmin[2];
   const double scale = t.hdr->scale;
-  const uint32_t mask = t.hdr->frame_cap - 1u;
+  const uint32_t frame_cap = t.hdr->frame_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double lim = (double)(1 << kVoxBits);
   const double inv_vs = 1.0 / vs;
-  static_assert(kVoxPerThread % 2 == 0, "rows are loaded two groups ahead");
-#pragma unroll 1
-  for (int g2 = 0; g2 < kVoxPerThread; g2 += 2) {
-   float raw[2][6];
-   bool live[2];
+  unsigned long long keys[kVoxPerThread];
+  uint32_t rows[kVoxPerThread];
+  bool act[kVoxPerThread];
 #pragma unroll
-   for (int h = 0; h < 2; ++h) {  // both groups' loads are in flight before either is used
-     const uint32_t i = tile_base + (uint32_t)((warp * kVoxPerThread + g2 + h) * 32 + lane);
-     live[h] = i < M;
-     if (live[h]) {
-       const float *p = xyz + 3 * (size_t)i, *c = rgb + 3 * (size_t)i;
-       raw[h][0] = __ldg(p); raw[h][1] = __ldg(p + 1); raw[h][2] = __ldg(p + 2);
-       raw[h][3] = __ldg(c); raw[h][4] = __ldg(c + 1); raw[h][5] = __ldg(c + 2);
-     }
-   }
-#pragma unroll
-   for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < kVoxPerThread; ++h) {
+    const uint32_t i = tile_base + (uint32_t)((warp * kVoxPerThread + h) * 32 + lane);
     VoxRun run;
-    run.key = kVoxEmpty;  // rows past the end / rejected rows: no run
+    run.key = kVoxNoKey;  // rows past the end / rejected rows: no run
     run.cnt_r = run.g_b = run.sx = run.sy = run.sz = 0ull;
-    if (live[h]) {
-      const double o0 = (double)raw[h][0] - vmin0, o1 = (double)raw[h][1] - vmin1, o2 = (double)raw[h][2] - vmin2;
+    if (i < M) {
+      const float *p = xyz + 3 * (size_t)i, *c = rgb + 3 * (size_t)i;
+      const float x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2);
+      const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+      const double o0 = (double)x0 - vmin0, o1 = (double)x1 - vmin1, o2 = (double)x2 - vmin2;
       // floor((p - vmin) / vs): correctly rounded quotient from the reciprocal (d2pc_math.h div_by_const)
       const double i0d = floor(div_by_const(o0, vs, inv_vs)), i1d = floor(div_by_const(o1, vs, inv_vs)),
                    i2d = floor(div_by_const(o2, vs, inv_vs));
       if (i0d >= 0.0 && i0d < lim && i1d >= 0.0 && i1d < lim && i2d >= 0.0 && i2d < lim) {
         run.key = ((unsigned long long)i0d << (2 * kVoxBits)) | ((unsigned long long)i1d << kVoxBits) |
                   (unsigned long long)i2d;
-        run.cnt_r = (1ull << 32) | (unsigned long long)(uint32_t)raw[h][3];
-        run.g_b = ((unsigned long long)(uint32_t)raw[h][4] << 32) | (unsigned long long)(uint32_t)raw[h][5];
+        run.cnt_r = (1ull << 32) | (unsigned long long)(uint32_t)c0;
+        run.g_b = ((unsigned long long)(uint32_t)c1 << 32) | (unsigned long long)(uint32_t)c2;
         run.sx = (unsigned long long)__double2ll_rn(o0 * scale);
         run.sy = (unsigned long long)__double2ll_rn(o1 * scale);
         run.sz = (unsigned long long)__double2ll_rn(o2 * scale);
@@ -225,83 +281,88 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
       }
     }
     const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-    if (tail && run.key != kVoxEmpty) vox_flush(t, mask, run, s_new, &s_nnew);
-   }
+    keys[h] = run.key;
+    rows[h] = i;
+    act[h] = tail && run.key != kVoxNoKey;
+    if (act[h]) vox_publish(t, run, i);   // in row order: a streaming write
   }
-  __syncthreads();
-  const uint32_t nn = s_nnew;
-  if (nn == 0) return;
-  if (threadIdx.x == 0) s_base = atomicAdd(&t.hdr->n_list, nn);
-  __syncthreads();
-  const uint32_t base = s_base;
-  for (uint32_t j = threadIdx.x; j < nn; j += kVoxThreads) t.list[base + j] = s_new[j];
+  __threadfence();   // one fence for the lane's rows: sums and keys are in place before any row can be found
+  vox_claim<kVoxPerThread>(t, frame_cap, keys, rows, act);
 }
 
-__global__ void __launch_bounds__(kVoxThreads, 2) vox_extract_kernel(VoxTable t, float *oxyz, float *orgb, int32_t *oidx,
-                                                                  uint32_t *ocount, const int32_t *err) {
-  const uint32_t V = t.hdr->n_list;
-  // CTAs past the occupied list have nothing to do (an unusable table has an empty list)
-  if (blockIdx.x * (uint32_t)kVoxTile >= V) return;
+// streams over the rows: representatives -> means -> compacted output rows
+__global__ void __launch_bounds__(kVoxThreads, 3) vox_extract_kernel(VoxTable t, const uint32_t *count, float *oxyz,
+                                                                     float *orgb, int32_t *oidx, uint32_t *ocount,
+                                                                     const int32_t *err) {
+  __shared__ uint32_t s_warp[kVoxThreads / 32];
+  __shared__ uint32_t s_base;
+  const uint32_t M = *count;
+  const uint32_t tile_base = blockIdx.x * (uint32_t)kVoxTile;
+  if (tile_base >= M || t.hdr->bad) return;  // uniform
   const bool failed = *err != 0;
-  const double inv_scale = 1.0 / t.hdr->scale;  // power of two: exact
-  const double vmin0 = t.hdr->vmin[0], vmin1 = t.hdr->vmin[1], vmin2 = t.hdr->vmin[2];
-  constexpr int E = kVoxPerThread;  // slots per thread, all loads issued before the first use
-  const uint32_t j0 = blockIdx.x * (uint32_t)kVoxTile + threadIdx.x;
-  {
-    uint32_t slot[E];
-    uint4 w[E][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t i0 = tile_base + 4u * (uint32_t)tid;   // 4 consecutive rows per thread
+  uint32_t f = 0;
+  if (i0 < M) f = *reinterpret_cast<const uint32_t *>(t.flags + i0);  // rows >= M were cleared (padding to 16)
+  const uint32_t mine = __popc(f & 0x01010101u);
+  uint32_t incl = mine;
 #pragma unroll
-    for (int k = 0; k < E; ++k) {
-      const uint32_t j = j0 + (uint32_t)k * kVoxThreads;
-      slot[k] = j < V ? t.list[j] : 0xFFFFFFFFu;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kVoxThreads / 32; ++w) {
+    const uint32_t x = s_warp[w];
+    if (w < warp) woff += x;
+    total += x;
+  }
+  if (tid == 0) s_base = (total && !failed) ? atomicAdd(&t.hdr->n_out, total) : 0u;
+  __syncthreads();
+  if (!failed && mine) {
+    uint32_t j = s_base + woff + incl - mine;
+    const double inv_scale = 1.0 / t.hdr->scale;  // power of two: exact
+    const double vmin0 = t.hdr->vmin[0], vmin1 = t.hdr->vmin[1], vmin2 = t.hdr->vmin[2];
+    unsigned long long w[4][6];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // all loads of the thread's representatives in flight together
+      if (!((f >> (8 * k)) & 1u)) continue;
+      const uint32_t row = i0 + (uint32_t)k;
+      const unsigned long long *a = t.acc + 5 * (size_t)row;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) w[k][c] = __ldcg(a + c);
+      w[k][5] = __ldcg(t.keys + row);
     }
 #pragma unroll
-    for (int k = 0; k < E; ++k) {
-      if (slot[k] == 0xFFFFFFFFu) continue;
-      const uint4 *e16 = reinterpret_cast<const uint4 *>(t.ent + slot[k]);
-      w[k][0] = e16[0]; w[k][1] = e16[1]; w[k][2] = e16[2];
-    }
-#pragma unroll
-    for (int k = 0; k < E; ++k) {
-      if (slot[k] == 0xFFFFFFFFu) continue;
-      const uint32_t j = j0 + (uint32_t)k * kVoxThreads;
-      uint4 *e16 = reinterpret_cast<uint4 *>(t.ent + slot[k]);
-      // leave the table clean for the next frame
-      e16[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-      e16[1] = make_uint4(0u, 0u, 0u, 0u);
-      e16[2] = make_uint4(0u, 0u, 0u, 0u);
-      if (failed) continue;
-      const uint4 w0 = w[k][0], w1 = w[k][1], w2 = w[k][2];
-      const unsigned long long key = ((unsigned long long)w0.y << 32) | w0.x;
-      const uint32_t cnt = w0.w, sr = w0.z, sg = w1.y, sb = w1.x;
-      const unsigned long long sx = ((unsigned long long)w1.w << 32) | w1.z;
-      const unsigned long long sy = ((unsigned long long)w2.y << 32) | w2.x;
-      const unsigned long long sz = ((unsigned long long)w2.w << 32) | w2.z;
-      const double n = (double)cnt;
+    for (int k = 0; k < 4; ++k) {
+      if (!((f >> (8 * k)) & 1u)) continue;
+      const unsigned long long cnt_r = w[k][0], g_b = w[k][1], sx = w[k][2], sy = w[k][3], sz = w[k][4], key = w[k][5];
+      const double n = (double)(uint32_t)(cnt_r >> 32);
       float *ox = oxyz + 3 * (size_t)j, *oc = orgb + 3 * (size_t)j;
       stg_stream_f1(ox + 0, (float)(vmin0 + ((double)(long long)sx * inv_scale) / n));
       stg_stream_f1(ox + 1, (float)(vmin1 + ((double)(long long)sy * inv_scale) / n));
       stg_stream_f1(ox + 2, (float)(vmin2 + ((double)(long long)sz * inv_scale) / n));
-      stg_stream_f1(oc + 0, (float)((double)sr / n));
-      stg_stream_f1(oc + 1, (float)((double)sg / n));
-      stg_stream_f1(oc + 2, (float)((double)sb / n));
+      stg_stream_f1(oc + 0, (float)((double)(uint32_t)cnt_r / n));
+      stg_stream_f1(oc + 1, (float)((double)(uint32_t)(g_b >> 32) / n));
+      stg_stream_f1(oc + 2, (float)((double)(uint32_t)g_b / n));
       if (oidx) {
         oidx[3 * (size_t)j + 0] = (int32_t)(key >> (2 * kVoxBits));
         oidx[3 * (size_t)j + 1] = (int32_t)((key >> kVoxBits) & ((1u << kVoxBits) - 1u));
         oidx[3 * (size_t)j + 2] = (int32_t)(key & ((1u << kVoxBits) - 1u));
       }
+      ++j;
     }
   }
-  // the last CTA publishes the count and resets the list for the next frame
+  // the last CTA with work publishes the count
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     __threadfence();
     const uint32_t ticket = atomicAdd(&t.hdr->done, 1u);
-    if (ticket == (V + kVoxTile - 1) / kVoxTile - 1) {  // CTAs with work
-      *ocount = failed ? 0u : V;
-      t.hdr->n_list = 0;
-      t.hdr->done = 0;
-      __threadfence();
+    if (ticket == (M + kVoxTile - 1) / kVoxTile - 1) {
+      *ocount = failed ? 0u : *reinterpret_cast<volatile uint32_t *>(&t.hdr->n_out);
     }
   }
 }
@@ -328,7 +389,7 @@ extern "C" int d2pc_voxel_table_init(const D2pcConfig *cfg, void *d_table, size_
   if (g.N >= kVoxMaxRows) return D2PC_ERR_UNSUPPORTED;
   const uint32_t cap = vox_capacity(g.N);
   if (table_bytes < vox_bytes(cap, g.N)) return D2PC_ERR_WORKSPACE_TOO_SMALL;
-  vox_init_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(vox_table(d_table, cap));
+  vox_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vox_table(d_table, cap, g.N));
   D2PC_CHECK_LAUNCH();
   return D2PC_OK;
 }
@@ -350,17 +411,19 @@ extern "C" int d2pc_voxel_enqueue(const D2pcConfig *cfg, double voxel_size, cons
   const uint32_t cap = vox_capacity(g.N);
   if (table_bytes < vox_bytes(cap, g.N)) return D2PC_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
-  VoxTable t = vox_table(d_table, cap);
+  VoxTable t = vox_table(d_table, cap, g.N);
   const uint32_t tiles = (g.N + kVoxTile - 1) / kVoxTile;
   for (int b = 0; b < cfg->batch; ++b) {
     const size_t ro = (size_t)b * g.N * 3;
     vox_begin_kernel<<<1, 32, 0, st>>>(t, d_count + b, d_bounds + 6 * b, voxel_size, d_vox_count + b,
                                        d_vox_error + b);
     D2PC_CHECK_LAUNCH();
+    vox_clear_kernel<<<148 * 4, 256, 0, st>>>(t, d_count + b);
+    D2PC_CHECK_LAUNCH();
     vox_insert_kernel<<<tiles, kVoxThreads, 0, st>>>(t, d_xyz + ro, d_rgb + ro, d_count + b, voxel_size,
                                                      d_vox_error + b);
     D2PC_CHECK_LAUNCH();
-    vox_extract_kernel<<<tiles, kVoxThreads, 0, st>>>(t, d_vox_xyz + ro, d_vox_rgb + ro,
+    vox_extract_kernel<<<tiles, kVoxThreads, 0, st>>>(t, d_count + b, d_vox_xyz + ro, d_vox_rgb + ro,
                                                         d_vox_idx ? d_vox_idx + ro : nullptr, d_vox_count + b,
                                                         d_vox_error + b);
     D2PC_CHECK_LAUNCH();

@@ -206,8 +206,10 @@ int d2pc_preview_enqueue(const D2pcConfig *cfg, const float *d_depth, void *d_wo
  *   d_xyz/d_rgb/d_count/d_bounds  outputs of d2pc_emit_enqueue (want_bounds = 1), row stride N;
  *                 colours must be the integral 0..255 values emit writes (their sums are kept exact)
  *   d_table       scratch of d2pc_voxel_table_bytes() bytes, 256-byte aligned, on which
- *                 d2pc_voxel_table_init() has run once after allocation (hash table of 64-byte
- *                 entries + occupied-slot list).  Every d2pc_voxel_enqueue leaves it clean again.
+ *                 d2pc_voxel_table_init() has run once after allocation: a table of 4-byte slots (8-bit
+ *                 fingerprint | 24-bit row of the voxel's representative row, small enough to stay in L2), and
+ *                 per-row keys, accumulators and flags that are only touched in row order (csrc/d2pc_voxel.cu).
+ *                 Cleared per frame by the call itself.
  *   d_vox_xyz/rgb float32 [batch, N, 3]; d_vox_idx int32 [batch, N, 3] or NULL;
  *   d_vox_count   uint32 [batch]; d_vox_error int32 [batch] (1 = index overflow, >= 2^21;
  *                 2 = table not initialised)
