@@ -132,13 +132,27 @@ class ClockSampler:
 
 def measured_traffic_per_frame():
     """dram__bytes_read.sum + dram__bytes_write.sum of emit_fast_kernel per 1080p frame, from the
-    committed `ncu --set full` capture (profiles/r01_emit_traffic.json); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_emit_traffic.json")
+    committed `ncu --set full` capture (profiles/r02_emit_traffic.json); None if absent."""
     try:
+        ps = [os.path.join(ROOT, "profiles", r + "_emit_traffic.json") for r in ("r02", "r01")]
+        p = [x for x in ps if os.path.exists(x)][0]
         d = json.load(open(p))
         return float(d["dram_bytes_per_frame"])
     except Exception:
         return None
+
+
+def pcie_ceiling(n_gpus):
+    """End-to-end ceiling of this pool's boxes in Mpoints/s for n_gpus GPUs copying concurrently: plain pinned
+    cudaMemcpyAsync in both directions at the pipeline's sizes (profiles/pcie_ceiling.py -> r02_pcie_ceiling.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")))
+        for r in d["runs"]:
+            if r["gpus"] == n_gpus and r["mode"] == "both":
+                return r
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -437,6 +451,13 @@ def run_ours(args):
                          "stats_ms_per_step": round(stats_ms, 4)},
             "clocks": clocks.summary(),
         }
+        ceil = pcie_ceiling(world)
+        if ceil and ceil.get("e2e_ceiling_mpoints_s"):
+            line["e2e"]["pcie_ceiling_mpoints_s"] = ceil["e2e_ceiling_mpoints_s"]
+            line["e2e"]["frac_of_pcie_ceiling"] = round(e2e_val / ceil["e2e_ceiling_mpoints_s"], 3)
+            line["e2e"]["pcie_ceiling_source"] = ("profiles/r02_pcie_ceiling.json: %d GPU(s) copying concurrently, plain pinned "
+                                                  "cudaMemcpyAsync both ways: %.1f GB/s D2H + %.1f GB/s H2D aggregate"
+                                                  % (world, ceil["d2h_gbs_aggregate"], ceil["h2d_gbs_aggregate"]))
         if extras:
             line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:

@@ -57,24 +57,37 @@ __global__ void __launch_bounds__(32) mask_prepare_kernel(KParams kp, EmitArgs e
 // per-pixel depth map only (4 B/px).  One warp per 1024-pixel tile: 8 independent 16 B loads per
 // lane, a warp reduction, no shared memory, no barrier.  Mode-0 frames evaluate the exact chain.
 constexpr int kCountWarps = 8;
+template <int STEP>
 __global__ void __launch_bounds__(kCountWarps * 32) mask_count_kernel(KParams kp, EmitArgs ea, uint32_t tiles_per_frame,
-                                                                     uint32_t total_tiles) {
+                                                                     uint32_t total_tiles, unsigned long long magic_w) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t t = blockIdx.x * (uint32_t)kCountWarps + (uint32_t)warp;
   if (t >= total_tiles) return;
   const uint32_t b = t / tiles_per_frame, tile = t - b * tiles_per_frame;
   const FrameState *fs = kp.state + b;
   if (fs->status != D2PC_FRAME_READY) return;
-  const uint32_t P = kp.g.P;
+  const uint32_t N = kp.g.N, W = (uint32_t)kp.g.W, NU = (uint32_t)kp.g.nu;
   const uint32_t tile_base = tile * (uint32_t)kEmitTile;
-  const float *src = kp.depth + (size_t)b * P + tile_base;
-  float4 r[8];
+  const float *frame = kp.depth + (size_t)b * kp.g.P;
+  float4 r[8];   // the four sampled depths of each of the lane's 8 row groups (same pixels as emit_fast_tile)
   bool ok[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint32_t q = 4u * (uint32_t)(j * 32 + lane);
-    ok[j] = tile_base + q < P;  // P % 4 == 0 on this path
-    if (ok[j]) r[j] = ldg_stream_f4(src + q);
+    const uint32_t p0 = tile_base + 4u * (uint32_t)(j * 32 + lane);
+    ok[j] = p0 < N;  // N % 4 == 0 on this path
+    if (!ok[j]) continue;
+    if (STEP == 1) {
+      r[j] = ldg_stream_f4(frame + p0);
+    } else {
+      const uint32_t jv = (uint32_t)(((unsigned long long)p0 * magic_w) >> 40), ju = p0 - jv * NU;
+      const float *src = frame + (size_t)(jv * (uint32_t)STEP) * W + ju * (uint32_t)STEP;
+      if (STEP == 2) {
+        const float4 da = ldg_stream_f4(src), db = ldg_stream_f4(src + 4);
+        r[j] = make_float4(da.x, da.z, db.x, db.z);
+      } else {
+        r[j] = make_float4(__ldg(src), __ldg(src + 4), __ldg(src + 8), __ldg(src + 12));
+      }
+    }
   }
   uint32_t cnt = 0;
   const MaskParams mp = load_mask(fs);
@@ -392,8 +405,8 @@ int emit_launch(const D2pcConfig &cfg, const KParams &kp_in, const EmitArgs &ea,
     D2PC_CHECK_LAUNCH();
   }
   // fast path: 3-channel image, 4 consecutive output rows per thread in one image row, vector loads.
-  // stride 1: W % 4 == 0; stride 2: W % 8 == 0; stride 4: W % 16 == 0 (unmasked only for strides > 1)
-  const bool fast = !smooth && cfg.img_c == 3 && (cfg.img_w % (4 * cfg.step)) == 0 && (cfg.step == 1 || !mask) &&
+  // stride 1: W % 4 == 0; stride 2: W % 8 == 0; stride 4: W % 16 == 0
+  const bool fast = !smooth && cfg.img_c == 3 && (cfg.img_w % (4 * cfg.step)) == 0 &&
                     (((uintptr_t)kp.depth & 15u) == 0u) && (((uintptr_t)ea.bgr & 3u) == 0u) && (kp.g.N & 3u) == 0u &&
                     ((unsigned long long)kp.g.N * (unsigned long long)kp.g.nu < (1ull << 40));
   if (mask || cfg.want_bounds) {
@@ -406,22 +419,25 @@ int emit_launch(const D2pcConfig &cfg, const KParams &kp_in, const EmitArgs &ea,
     D2PC_CHECK_LAUNCH();
   }
   if (fast) {
-    if (mask) {
-      const uint32_t total_tiles = kp.emit_tiles * (uint32_t)nb;
-      mask_count_kernel<<<(total_tiles + kCountWarps - 1) / kCountWarps, kCountWarps * 32, 0, st>>>(kp, ea, kp.emit_tiles,
-                                                                                                   total_tiles);
-      D2PC_CHECK_LAUNCH();
-      mask_offsets_kernel<<<nb, 1024, 0, st>>>(kp, ea.count);
-      D2PC_CHECK_LAUNCH();
-    }
     FastArgs fa;
     fa.tiles_per_frame = kp.emit_tiles;
     fa.total_tiles = kp.emit_tiles * (uint32_t)nb;
     fa.batch = (uint32_t)nb;
     fa.magic_w = ((1ull << 40) + (unsigned long long)kp.g.nu - 1ull) / (unsigned long long)kp.g.nu;
     fa.pc_simple = consts_simple(ea.pc) ? 1 : 0;
+    if (mask) {
+      const uint32_t total_tiles = fa.total_tiles, cg = (total_tiles + kCountWarps - 1) / kCountWarps;
+      if (cfg.step == 1) mask_count_kernel<1><<<cg, kCountWarps * 32, 0, st>>>(kp, ea, kp.emit_tiles, total_tiles, fa.magic_w);
+      else if (cfg.step == 2) mask_count_kernel<2><<<cg, kCountWarps * 32, 0, st>>>(kp, ea, kp.emit_tiles, total_tiles, fa.magic_w);
+      else mask_count_kernel<4><<<cg, kCountWarps * 32, 0, st>>>(kp, ea, kp.emit_tiles, total_tiles, fa.magic_w);
+      D2PC_CHECK_LAUNCH();
+      mask_offsets_kernel<<<nb, 1024, 0, st>>>(kp, ea.count);
+      D2PC_CHECK_LAUNCH();
+    }
     int rcl;
-    if (mask) rcl = launch_emit_fast<1, true, 5>(kp, ea, fa, st);
+    if (mask) rcl = cfg.step == 1 ? launch_emit_fast<1, true, 5>(kp, ea, fa, st)
+                  : cfg.step == 2 ? launch_emit_fast<2, true, 5>(kp, ea, fa, st)
+                                  : launch_emit_fast<4, true, 5>(kp, ea, fa, st);
     else if (cfg.step == 1) rcl = launch_emit_fast<1, false, 6>(kp, ea, fa, st);
     else if (cfg.step == 2) rcl = launch_emit_fast<2, false, 6>(kp, ea, fa, st);
     else rcl = launch_emit_fast<4, false, 6>(kp, ea, fa, st);

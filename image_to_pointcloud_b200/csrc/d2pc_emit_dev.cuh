@@ -144,8 +144,9 @@ __device__ __forceinline__ uint32_t warp_first_true(uint32_t lo, uint32_t hi, Pr
 // One tile of 1024 consecutive output rows per CTA, 4 consecutive rows per thread (they share an
 // image row).  STEP 1: one 16 B depth load + 12 colour bytes; STEP 2 / 4 (density medium / low):
 // the same tiling over the strided output grid, loading only the sectors that hold sampled
-// pixels.  The depth map is always per-pixel here (the scan materialises a resized map).  MASK: depth-range / non-finite mask with ordered
-// compaction (CTA scan + decoupled look-back over the frame's tiles, tiles dispatched in order).
+// pixels.  The depth map is always per-pixel here (the scan materialises a resized map).  MASK (any stride):
+// depth-range / non-finite mask with ordered compaction; the tile's first output row comes from the per-tile
+// kept counts that mask_count_kernel + mask_offsets_kernel computed over the same sampled pixels.
 // High occupancy matters more than per-thread ILP here (measured: 6 CTAs/SM beat 3-5 and beat a
 // persistent register-prefetching variant), hence MIN_BLOCKS.
 struct FastArgs {
@@ -180,7 +181,6 @@ struct EmitSmall {  // static shared scratch of one emit tile
 template <int STEP, bool MASK, bool BOUNDS, typename NormFn>
 __device__ __forceinline__ bool emit_fast_tile(const KParams &kp, const EmitArgs &ea, const FastArgs &fa, uint32_t b,
                                                uint32_t tile, float *s_stage, EmitSmall &es, NormFn norm_fn) {
-  static_assert(STEP == 1 || !MASK, "the masked fast path is stride 1 only");
   uint32_t *s_warp = es.warp;
   uint32_t (*s_b)[kEmitThreads / 32] = es.b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -427,28 +427,57 @@ __device__ __forceinline__ void select_finish(FrameState *fs, SelShared *sh, int
   }
 }
 
-// part k of K of bracket br of frame b.  s_slice: slice_cap floats of shared memory (>= 2 << 11 words, which the
-// general selection needs).  spin(ptr, pred) -> bool is the caller's bounded wait (false: abort).  Returns false on abort.
-template <typename Spin>
-__device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, uint32_t k, uint32_t K, float *s_slice,
-                                            uint32_t slice_cap, SelPartSmall &ss, Spin spin) {
+// The cooperative selection in two steps.  Step A (select_phase_a): classify the slice, add to the global histogram;
+// the part that finishes last resolves the ranks and publishes the wanted buckets (or finishes the bracket if no
+// collect is needed).  Step C (select_phase_c): collect the members of the wanted buckets; the part that finishes
+// last picks the exact keys and finishes the bracket.  Inside an index-ordered kernel the two steps run in one CTA
+// with a bounded wait between them (select_part, slice cached in shared memory); as two launches (select_a_kernel /
+// select_c_kernel) nothing waits at all.
+//   s_slice: slice_cap floats of shared memory (>= 2 << 11 words, which the general selection needs).
+struct SelCommon {
+  FrameState *fs;
+  SelShared *sh;
+  const float *q;
+  uint32_t n, qcap, nqueue, nq, L, U, lo0, hi0, span, s_lo, m;
+  float Lf, Uf;
+  int shift;
+  bool cached;
+};
+__device__ __forceinline__ SelCommon select_common(const KParams &kp, int b, int br, uint32_t k, uint32_t K, uint32_t slice_cap) {
+  SelCommon c;
+  c.fs = kp.state + b;
+  c.sh = kp.sel + b;
+  volatile FrameState *vfs = c.fs;
+  c.n = kp.g.P; c.qcap = kp.cand_cap;
+  c.q = reinterpret_cast<const float *>(kp.cand) + ((size_t)b * 2 + br) * c.qcap;
+  c.nqueue = vfs->nqueue[br];
+  c.nq = min(c.nqueue, c.qcap);
+  c.L = c.fs->brL[br]; c.U = c.fs->brU[br];
+  c.Lf = bracket_lo_float(c.L); c.Uf = bracket_hi_float(c.U);
+  c.lo0 = c.L > 0u ? c.L - 1u : 0u;
+  c.hi0 = c.U < 0xFFFFFFFFu ? c.U + 1u : c.U;
+  c.span = c.hi0 - c.lo0;
+  c.shift = fast_shift(c.span);
+  const uint32_t chunk = (c.nq + K - 1u) / K;
+  c.s_lo = min(c.nq, k * chunk);
+  c.m = min(c.nq, c.s_lo + chunk) - c.s_lo;
+  c.cached = chunk <= slice_cap;
+  return c;
+}
+
+// returns 0: not the last part of step A; 1: last, buckets published (collect needed); 2: last, bracket finished
+__device__ __forceinline__ int select_phase_a(const KParams &kp, int b, int br, uint32_t k, uint32_t K, float *s_slice,
+                                              uint32_t slice_cap, SelPartSmall &ss) {
   const int tid = threadIdx.x, nthr = blockDim.x;
-  FrameState *fs = kp.state + b;
-  SelShared *sh = kp.sel + b;
-  volatile FrameState *vfs = fs;
-  const uint32_t n = kp.g.P, qcap = kp.cand_cap;
-  const float *q = reinterpret_cast<const float *>(kp.cand) + ((size_t)b * 2 + br) * qcap;
-  const uint32_t nqueue = vfs->nqueue[br];
-  const uint32_t nq = min(nqueue, qcap);
-  const uint32_t L = fs->brL[br], U = fs->brU[br];
-  const float Lf = bracket_lo_float(L), Uf = bracket_hi_float(U);
-  const uint32_t lo0 = L > 0u ? L - 1u : 0u;
-  const uint32_t hi0 = U < 0xFFFFFFFFu ? U + 1u : U;
-  const uint32_t span = hi0 - lo0;
-  const int shift = fast_shift(span);
-  const uint32_t chunk = (nq + K - 1u) / K;
-  const uint32_t s_lo = min(nq, k * chunk), s_hi = min(nq, s_lo + chunk), m = s_hi - s_lo;
-  const bool cached = chunk <= slice_cap;
+  const SelCommon cm = select_common(kp, b, br, k, K, slice_cap);
+  FrameState *fs = cm.fs;
+  SelShared *sh = cm.sh;
+  const float *q = cm.q;
+  const uint32_t n = cm.n, qcap = cm.qcap, nqueue = cm.nqueue, L = cm.L, U = cm.U, lo0 = cm.lo0, span = cm.span,
+                 s_lo = cm.s_lo, m = cm.m;
+  const float Lf = cm.Lf, Uf = cm.Uf;
+  const int shift = cm.shift;
+  const bool cached = cm.cached;
   if (tid < 6) ss.c[tid] = 0u;
   __syncthreads();
   {  // phase A: classify the slice, histogram of the inside keys
@@ -546,14 +575,22 @@ __device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, ui
         *reinterpret_cast<volatile uint32_t *>(&sh->bin_ready[br]) = 2u;
       }
     }
-    if (!collect) return true;
-  } else {
-    if (tid == 0) ss.flag_spin = spin(&sh->bin_ready[br], [](uint32_t v) { return v != 0u; }) ? 1u : 0u;
-    __syncthreads();
-    if (!ss.flag_spin) return false;
-    if (*reinterpret_cast<volatile uint32_t *>(&sh->bin_ready[br]) == 2u) return true;
+    return collect ? 1 : 2;
   }
-  __syncthreads();
+  return 0;
+}
+
+__device__ __forceinline__ void select_phase_c(const KParams &kp, int b, int br, uint32_t k, uint32_t K,
+                                               float *s_slice, uint32_t slice_cap, bool slice_is_cached, SelPartSmall &ss) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const SelCommon cm = select_common(kp, b, br, k, K, slice_cap);
+  FrameState *fs = cm.fs;
+  SelShared *sh = cm.sh;
+  const float *q = cm.q;
+  const uint32_t n = cm.n, nq = cm.nq, lo0 = cm.lo0, hi0 = cm.hi0, s_lo = cm.s_lo, m = cm.m;
+  const float Lf = cm.Lf, Uf = cm.Uf;
+  const int shift = cm.shift;
+  const bool cached = cm.cached && slice_is_cached;
   // phase C: members of the wanted buckets in this slice -> the frame's global lists
   {
     volatile SelShared *vsh = sh;
@@ -583,7 +620,7 @@ __device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, ui
     __threadfence();
   }
   __syncthreads();
-  if (ss.flag_c != K - 1u) return true;
+  if (ss.flag_c != K - 1u) return;
   // last of phase C: exact pick inside the buckets
   {
     volatile SelShared *vsh = sh;
@@ -625,6 +662,23 @@ __device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, ui
     }
     if (tid == 0) select_finish(fs, sh, br, n, key, fail);
   }
+}
+
+// both steps in one CTA (index-ordered kernels).  spin(ptr, pred) -> bool is the caller's bounded wait (false: abort).
+template <typename Spin>
+__device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, uint32_t k, uint32_t K, float *s_slice,
+                                            uint32_t slice_cap, SelPartSmall &ss, Spin spin) {
+  const int st = select_phase_a(kp, b, br, k, K, s_slice, slice_cap, ss);   // uniform over the CTA
+  if (st == 2) return true;
+  SelShared *sh = kp.sel + b;
+  if (st == 0) {
+    if (threadIdx.x == 0) ss.flag_spin = spin(&sh->bin_ready[br], [](uint32_t v) { return v != 0u; }) ? 1u : 0u;
+    __syncthreads();
+    if (!ss.flag_spin) return false;
+    if (*reinterpret_cast<volatile uint32_t *>(&sh->bin_ready[br]) == 2u) return true;
+  }
+  __syncthreads();
+  select_phase_c(kp, b, br, k, K, s_slice, slice_cap, true, ss);
   return true;
 }
 

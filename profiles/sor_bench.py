@@ -1,5 +1,7 @@
 """Row f1 timing: statistical outlier removal (k = 20, std_ratio = 2) on device-resident clouds produced by the
-stage itself, CUDA events around d2pc_sor_enqueue (+ the bounds pass).   python profiles/sor_bench.py"""
+stage itself, CUDA events around d2pc_sor_enqueue (+ the bounds pass), and beside it the CPU baseline on the same
+clouds: the oracle (scipy cKDTree k-NN + Open3D's statistics; Open3D itself is not installed) on 1 core and on all
+host cores (cKDTree.query(workers=-1)).   python profiles/sor_bench.py [--no-cpu]"""
 import json
 import os
 import sys
@@ -11,7 +13,24 @@ import image_to_pointcloud_b200 as m  # noqa: E402
 from profiles.voxel_sweep import depth_maps  # noqa: E402
 
 
-def bench(iters=5):
+def cpu_baseline(points_np, cores):
+    """Seconds of the oracle's k-NN + statistics on `cores` host cores (-1 = all)."""
+    import time
+
+    import numpy as np
+    from scipy.spatial import cKDTree
+    p = np.ascontiguousarray(points_np, dtype=np.float64)
+    t0 = time.perf_counter()
+    dist, _ = cKDTree(p).query(p, k=20, workers=cores)
+    avg = dist.sum(axis=1) / 20
+    pos = avg > 0
+    mean = avg[pos].sum() / len(p)
+    std = np.sqrt((((avg - mean) ** 2) * pos).sum() / (len(p) - 1))
+    keep = np.nonzero(pos & (avg < mean + 2.0 * std))[0]
+    return time.perf_counter() - t0, len(keep)
+
+
+def bench(iters=5, cpu=True):
     dev = torch.device("cuda", 0)
     out = {}
     for name, (H, W, dens) in {"480p_medium": (480, 640, "medium"), "1080p_medium": (1080, 1920, "medium"),
@@ -33,10 +52,18 @@ def bench(iters=5):
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / iters
-            out[f"{name}_{kind}"] = {"points": int(xyz.shape[0]), "kept": int(p.shape[0]), "ms": round(ms, 3),
-                                     "mpoints_per_s": round(xyz.shape[0] / ms / 1e3, 1)}
+            row = {"points": int(xyz.shape[0]), "kept": int(p.shape[0]), "ms": round(ms, 3),
+                   "mpoints_per_s": round(xyz.shape[0] / ms / 1e3, 1)}
+            if cpu and name != "1080p_high" or (cpu and kind == "scene"):
+                pts = xyz.cpu().numpy()
+                t1, k1 = cpu_baseline(pts, 1)
+                tn, kn = cpu_baseline(pts, -1)
+                row["cpu_oracle_scipy"] = {"s_1_core": round(t1, 3), "s_all_cores": round(tn, 3), "cores": os.cpu_count(),
+                                           "kept": k1, "speedup_vs_all_cores": round(tn * 1e3 / ms, 1)}
+            out[f"{name}_{kind}"] = row
     return out
 
 
 if __name__ == "__main__":
-    print(json.dumps({"workload": "SOR k=20 std_ratio=2 on the stage's own clouds (scene / uniform-random depth)", "sor": bench()}))
+    print(json.dumps({"workload": "SOR k=20 std_ratio=2 on the stage's own clouds (scene / uniform-random depth)",
+                      "sor": bench(cpu="--no-cpu" not in sys.argv)}))

@@ -154,3 +154,25 @@ def test_stale_library_is_refused(monkeypatch, tmp_path):
     monkeypatch.setattr(build, "stored_digest", lambda: "0" * 64)
     with pytest.raises(RuntimeError, match="stale"):
         _lib.load_library()
+
+
+@pytest.mark.parametrize("density", ["medium", "low"])
+@pytest.mark.parametrize("kind", ["uniform", "scene", "ties"])
+def test_masked_strided_fast_path(density, kind):
+    """density medium / low with a depth-range mask (what the reference UI's default density gives with the
+    extension on) runs the vectorised masked emit: rows, order and count equal the oracle's post-filter."""
+    import image_to_pointcloud_b200 as m
+    from oracle import d2pc_oracle as O
+    H, W = 150, 224     # W % 16 == 0: the fast path for both strides; H not a multiple of the stride
+    for h, w in ((H, W), (97, 131)):
+        img = cases.make_image(H, W, 77)
+        dep = cases.make_depth(h, w, 78, kind)
+        for zr in ((0.5, 9.5), (9.0, 9.99), (0.0, 0.2)):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                po, co = O.depth_to_point_cloud(img, dep, density=density)
+            keep = O.range_mask(po, *zr)
+            p, c = m.depth_to_point_cloud(img, dep, density=density, z_range=zr, device="cuda:0")
+            assert p.shape[0] == int(keep.sum()), (h, w, zr)
+            assert np.array_equal(p.view(np.uint32), po[keep].view(np.uint32)), (h, w, zr)
+            assert np.array_equal(c, co[keep]), (h, w, zr)
