@@ -57,6 +57,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    path = path or os.environ.get("D2PC_LIBRARY") or None   # measurement aid: A/B runs against another build
     p = path or LIB_PATH
     if path is None:
         try:

@@ -251,7 +251,7 @@ int validate_config(const D2pcConfig *cfg);   // d2pc_api.cu
 int check_workspace(const D2pcConfig *cfg, const void *ws, size_t ws_bytes);
 int stats_prepare();
 int taps_launch(const KParams &kp, cudaStream_t st);
-constexpr int kStatsSample = 1, kStatsScanSelect = 2;
+constexpr int kStatsSample = 1, kStatsScan = 2, kStatsSelect = 4, kStatsScanSelect = kStatsScan | kStatsSelect;
 int stats_launch(KParams kp, cudaStream_t st, int phases);
 int status_launch(const KParams &kp, int32_t *d_status, int32_t *d_any, cudaStream_t st);
 // d2pc_emit.cu

@@ -304,9 +304,14 @@ int path_body(D2pcPath *p, const PathArgs &a, cudaStream_t s_main) {
   if (const char *h = getenv("D2PC_HINTS")) kp.hints = atoi(h);  // measurement aid
   const EmitArgs ea = make_emit_args(cfg, a.d_bgr, a.d_xyz, a.d_rgb, a.d_count);
   int rc;
-  if ((rc = ensure_events(p, 1 + 2 * (size_t)n_sub)) != D2PC_OK) return rc;
+  if ((rc = ensure_events(p, 1 + 3 * (size_t)n_sub)) != D2PC_OK) return rc;
   cudaEvent_t ev_fork = p->events[0];
-  cudaEvent_t *ev_stats = &p->events[1], *ev_emit = &p->events[1 + n_sub];
+  cudaEvent_t *ev_stats = &p->events[1], *ev_emit = &p->events[1 + n_sub], *ev_scan = &p->events[1 + 2 * n_sub];
+  // Staggered chain (measurement aid, D2PC_PATH_STAGGER=1): scan(k + 1) starts when scan(k) has finished, so the
+  // latency-bound selection of sub-batch k runs under the scan of sub-batch k + 1 and the emits behind it instead
+  // of all sub-batches moving in lockstep.  Measured slower than one stage (128 x 1080p: 1.65 ms staggered in
+  // halves against 1.57 ms): kernels that share the GPU each slow down by what the overlap would have saved.
+  const bool stagger = overlap && n_aux > 1 && env_int("D2PC_PATH_STAGGER", 0, 0, 1) != 0;
   if ((rc = taps_launch(kp, s_main)) != D2PC_OK) return rc;
   if (sample_first) {  // the sample depends on the input only: all frames at once, off the per-stage chain
     if ((rc = stats_launch(kp, s_main, kStatsSample)) != D2PC_OK) return rc;
@@ -323,7 +328,13 @@ int path_body(D2pcPath *p, const PathArgs &a, cudaStream_t s_main) {
     cudaStream_t s_stats = overlap ? p->s_aux[k % n_aux] : s_main;
     cudaStream_t s_em = (overlap && n_emit > 1) ? p->s_emit[k % n_emit] : s_main;
     if (overlap && k >= window) PATH_CUDA(cudaStreamWaitEvent(s_stats, ev_emit[k - window], 0));
-    if ((rc = stats_launch(ks, s_stats, sample_first ? kStatsScanSelect : (kStatsSample | kStatsScanSelect))) != D2PC_OK)
+    if (stagger) {
+      if (!sample_first && (rc = stats_launch(ks, s_stats, kStatsSample)) != D2PC_OK) return rc;
+      if (k > 0) PATH_CUDA(cudaStreamWaitEvent(s_stats, ev_scan[k - 1], 0));
+      if ((rc = stats_launch(ks, s_stats, kStatsScan)) != D2PC_OK) return rc;
+      PATH_CUDA(cudaEventRecord(ev_scan[k], s_stats));
+      if ((rc = stats_launch(ks, s_stats, kStatsSelect)) != D2PC_OK) return rc;
+    } else if ((rc = stats_launch(ks, s_stats, sample_first ? kStatsScanSelect : (kStatsSample | kStatsScanSelect))) != D2PC_OK)
       return rc;
     if (overlap) {
       PATH_CUDA(cudaEventRecord(ev_stats[k], s_stats));

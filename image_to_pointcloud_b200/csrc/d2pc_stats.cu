@@ -381,6 +381,26 @@ __global__ void __launch_bounds__(kSelectThreads, 2) select_kernel(KParams kp) {
   select_bracket(kp, blockIdx.y, blockIdx.x, s_sel, ss);
 }
 
+// The same selection by K CTAs per (frame, bracket) as two launches (nothing waits): step A classifies the slices
+// (shared-memory bucket histograms, merged into the frame's global one) and the last CTA of a bracket locates the
+// wanted buckets; step C collects their members and the last CTA picks the exact keys.  For large frames / few
+// frames, where one CTA per bracket walking a quarter of a million queued values twice is the whole stage
+// (4K x 16: 166 us).
+constexpr int kCoopThreads = 512;
+constexpr uint32_t kCoopSmemWords = 2u << 11;   // bucket histogram in step A; lists / general selection in step C
+__global__ void __launch_bounds__(kCoopThreads) select_a_kernel(KParams kp, uint32_t K) {
+  extern __shared__ uint32_t s_sel[];
+  __shared__ SelPartSmall ss;
+  select_phase_a<true>(kp, blockIdx.z, blockIdx.y, blockIdx.x, K, reinterpret_cast<float *>(s_sel), 0u, ss);
+}
+__global__ void __launch_bounds__(kCoopThreads) select_c_kernel(KParams kp, uint32_t K) {
+  extern __shared__ uint32_t s_sel[];
+  __shared__ SelPartSmall ss;
+  const int b = blockIdx.z, br = blockIdx.y;
+  if (*reinterpret_cast<volatile uint32_t *>(&kp.sel[b].bin_ready[br]) != 1u) return;  // finished in step A
+  select_phase_c(kp, b, br, blockIdx.x, K, reinterpret_cast<float *>(s_sel), 0u, false, ss);
+}
+
 // ------------------------------------------------------------------------------------------
 // stats_ordered_kernel: scan and exact selection of a whole batch in ONE launch
 // ------------------------------------------------------------------------------------------
@@ -708,7 +728,7 @@ int stats_launch(KParams kp, cudaStream_t st, int phases) {
   // of 66 us for a 1080p frame).  Batches: the selection's waiting CTAs would hold slots the scan needs (measured
   // 0.45 ms against 0.32 ms per 128 frames), so scan and selection stay two launches there.
   const char *mode = getenv("D2PC_STATS_ORDERED");  // measurement aid: "0" never, "1" always
-  const bool ordered = mode ? atoi(mode) != 0 : nb <= 2;
+  const bool ordered = (phases & kStatsScanSelect) == kStatsScanSelect && (mode ? atoi(mode) != 0 : nb <= 2);
   if (kp.g.native && kp.g.P > (uint32_t)kSortCap && ordered) {
     const uint32_t ns = (kp.g.P + kTilePx - 1) / kTilePx;
     uint32_t K = (kp.cand_cap + kStatsSliceCap - 1u) / kStatsSliceCap;
@@ -720,7 +740,8 @@ int stats_launch(KParams kp, cudaStream_t st, int phases) {
       return D2PC_OK;
     }
   }
-  if (kp.g.native) {
+  if (!(phases & kStatsScan)) {
+  } else if (kp.g.native) {
     scan_native_kernel<kTilePerThread><<<dim3((kp.g.P + kTilePx - 1) / kTilePx, nb), kScanThreads, sizeof(ScanTileSmem), st>>>(kp, vec_ok);
   } else {
     // tiled kernel: needs 16 B-aligned rows of the resized map and every tile's source rows in shared memory
@@ -738,8 +759,27 @@ int stats_launch(KParams kp, cudaStream_t st, int phases) {
     }
   }
   D2PC_CHECK_LAUNCH();
-  select_kernel<<<dim3(2, nb), kSelectThreads, (size_t)kSelectSmemWords * sizeof(uint32_t), st>>>(kp);
-  D2PC_CHECK_LAUNCH();
+  if (phases & kStatsSelect) {
+    // One CTA per bracket is a chain of latencies (1080p: 52 us, 4K: 166 us) that only pays when the batch
+    // fills the GPU with such CTAs (2 nb >= ~150).  Smaller batches and 4K frames split each bracket over K
+    // CTAs, two launches (measured, statistics of 16 frames: 1080p 0.105 -> 0.085 ms, 4K 0.300 -> 0.193 ms;
+    // 128 x 1080p would lose: 0.316 -> 0.36 ms).
+    const char *cm = getenv("D2PC_SELECT_COOP");  // measurement aid: "0" never, K > 0 always with K parts
+    uint32_t K = 296u / (2u * (uint32_t)nb);
+    if (K > 16u) K = 16u;
+    if (kp.g.P >= 4u * 1024u * 1024u && K < 4u) K = 4u;
+    if (K < 4u) K = 0u;
+    if (cm) K = (uint32_t)atoi(cm);
+    if (K > 64u) K = 64u;
+    if (K >= 2u && kp.g.P > (uint32_t)kSortCap) {
+      select_a_kernel<<<dim3(K, 2, nb), kCoopThreads, kCoopSmemWords * sizeof(uint32_t), st>>>(kp, K);
+      D2PC_CHECK_LAUNCH();
+      select_c_kernel<<<dim3(K, 2, nb), kCoopThreads, kCoopSmemWords * sizeof(uint32_t), st>>>(kp, K);
+    } else {
+      select_kernel<<<dim3(2, nb), kSelectThreads, (size_t)kSelectSmemWords * sizeof(uint32_t), st>>>(kp);
+    }
+    D2PC_CHECK_LAUNCH();
+  }
   return D2PC_OK;
 }
 

@@ -466,6 +466,10 @@ __device__ __forceinline__ SelCommon select_common(const KParams &kp, int b, int
 }
 
 // returns 0: not the last part of step A; 1: last, buckets published (collect needed); 2: last, bracket finished
+// LOCAL_HIST (stand-alone two-launch selection, slice not cached): the slice's bucket histogram is built in
+// shared memory (s_slice, kSelBins words) and only its non-zero buckets are added to the frame's global one --
+// a few thousand spread-out L2 reductions per CTA instead of one contended L2 atomic per inside value.
+template <bool LOCAL_HIST = false>
 __device__ __forceinline__ int select_phase_a(const KParams &kp, int b, int br, uint32_t k, uint32_t K, float *s_slice,
                                               uint32_t slice_cap, SelPartSmall &ss) {
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -477,12 +481,14 @@ __device__ __forceinline__ int select_phase_a(const KParams &kp, int b, int br, 
                  s_lo = cm.s_lo, m = cm.m;
   const float Lf = cm.Lf, Uf = cm.Uf;
   const int shift = cm.shift;
-  const bool cached = cm.cached;
+  const bool cached = cm.cached && !LOCAL_HIST;
   if (tid < 6) ss.c[tid] = 0u;
+  if (LOCAL_HIST)
+    for (uint32_t i = tid; i < kSelBins; i += nthr) reinterpret_cast<uint32_t *>(s_slice)[i] = 0u;
   __syncthreads();
   {  // phase A: classify the slice, histogram of the inside keys
     uint32_t c_eqL = 0, c_in = 0, c_eqU = 0, c_below = 0, c_nf = 0;
-    uint32_t *hist = sh->hist[br];
+    uint32_t *hist = LOCAL_HIST ? reinterpret_cast<uint32_t *>(s_slice) : sh->hist[br];
     auto visit = [&](float v) {
       if (!(fabsf(v) < __int_as_float(0x7F800000))) c_nf += 1u + ((v != v) ? 0x10000u : 0u);
       else if (v < Lf) c_below++;
@@ -521,6 +527,15 @@ __device__ __forceinline__ int select_phase_a(const KParams &kp, int b, int br, 
     }
   }
   __syncthreads();
+  if (LOCAL_HIST) {
+    const uint32_t *lh = reinterpret_cast<const uint32_t *>(s_slice);
+    for (uint32_t i = tid; i < kSelBins; i += nthr) {
+      const uint32_t h = lh[i];
+      if (h) atomicAdd(&sh->hist[br][i], h);
+    }
+    __threadfence();
+    __syncthreads();   // the ticket below (thread 0) follows every thread's reductions
+  }
   if (tid == 0) {
     for (int c = 0; c < 6; ++c)
       if (ss.c[c]) atomicAdd(&sh->counts[br][c], ss.c[c]);
@@ -668,7 +683,7 @@ __device__ __forceinline__ void select_phase_c(const KParams &kp, int b, int br,
 template <typename Spin>
 __device__ __forceinline__ bool select_part(const KParams &kp, int b, int br, uint32_t k, uint32_t K, float *s_slice,
                                             uint32_t slice_cap, SelPartSmall &ss, Spin spin) {
-  const int st = select_phase_a(kp, b, br, k, K, s_slice, slice_cap, ss);   // uniform over the CTA
+  const int st = select_phase_a<false>(kp, b, br, k, K, s_slice, slice_cap, ss);   // uniform over the CTA
   if (st == 2) return true;
   SelShared *sh = kp.sel + b;
   if (st == 0) {

@@ -17,6 +17,13 @@ VARIANTS = {
     "medium_dav2": (1080, 1920, 518, 924, 16, None, "medium"),
     "mask4k_1": (2160, 3840, 2160, 3840, 1, (0.5, 9.5), "high"),
     "scene4k_1": (2160, 3840, 2160, 3840, 1, (0.5, 9.5), "high"),
+    "native128": (1080, 1920, 1080, 1920, 128, None, "high"),
+    "native4k16": (2160, 3840, 2160, 3840, 16, None, "high"),
+    "mask4k16": (2160, 3840, 2160, 3840, 16, (0.5, 9.5), "high"),
+    "dav2_64": (1080, 1920, 518, 924, 64, None, "high"),
+    "mask64": (1080, 1920, 1080, 1920, 64, (0.5, 9.5), "high"),
+    "mask_medium64": (1080, 1920, 1080, 1920, 64, (0.5, 9.5), "medium"),
+    "medium_dav2_64": (1080, 1920, 518, 924, 64, None, "medium"),
     "scene_mask": (1080, 1920, 1080, 1920, 16, (2.0, 6.0), "high"),   # coherent mask: whole tiles kept / dropped
 }
 
@@ -48,6 +55,20 @@ def main():
     b.record()
     torch.cuda.synchronize()
     print(name, "ms/iter", a.elapsed_time(b) / iters, "kept", int(cnt.sum()), "of", B * eng.points_per_frame(cfg))
+    if os.environ.get("TIMELINE"):  # per-kernel start / duration of one iteration (CUPTI through torch.profiler)
+        import json
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            eng.enqueue_stats(cfg, depth, s)
+            eng.enqueue_emit(cfg, depth, bgr, xyz, rgb, cnt, None, s)
+            torch.cuda.synchronize()
+        path = "/tmp/_tl_%s.json" % name
+        prof.export_chrome_trace(path)
+        ev = sorted((e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"), key=lambda e: e["ts"])
+        t0 = ev[0]["ts"]
+        for e in ev:
+            nm = e["name"].split("(")[0].replace("void d2pc::", "").replace("d2pc::", "")[:40]
+            print("  %9.1f %8.1f  %-40s %s" % (e["ts"] - t0, e["dur"], nm, e["args"].get("grid")))
     if len(sys.argv) > 3:  # voxel sizes: time emit(with bounds)+voxel per size
         from image_to_pointcloud_b200.engine import EmitResult
         cfgb = eng.make_config(density=dens, z_range=zr, want_bounds=True)

@@ -80,8 +80,8 @@ def test_reference_signature_and_errors():
     import numpy as np
     with pytest.raises(KeyError):  # unknown density -> KeyError before any device work (app.py:226)
         m.depth_to_point_cloud(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4), np.float32), density="ultra")
-    with pytest.raises(TypeError):  # a float64 map would be interpolated in float64 by the reference: refused
-        m.depth_to_point_cloud(np.zeros((4, 4, 3), np.uint8), np.zeros((3, 5), np.float64))
+    with pytest.raises(TypeError):  # cv2 rounds an interpolated integer map back to integers: refused, not approximated
+        m.depth_to_point_cloud(np.zeros((4, 4, 3), np.uint8), np.zeros((3, 5), np.uint16))
 
 
 def test_shard_frames_partition():

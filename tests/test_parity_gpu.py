@@ -130,6 +130,27 @@ def test_resized_batch_all_strides(m):
             assert_bits_equal(res.rgb[b].cpu().numpy(), co, f"{dens} frame {b}")
 
 
+def test_float64_depth_that_needs_a_resize_is_cast_first(m):
+    """Documented deviation (api.check_depth_dtype): a float64 map is cast to float32 and then interpolated like
+    a float32 map (bit-exact against the oracle on the cast map); the reference would interpolate in float64 --
+    the result stays inside the 1e-5 tolerance of that."""
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (90, 120, 3), dtype=np.uint8)
+    dep = rng.random((41, 57)) * 20
+    p, c = m.depth_to_point_cloud(img, dep, density="high")
+    po, co = _oracle(img, dep.astype(np.float32), density="high")
+    assert_bits_equal(p, po, "float64 depth")
+    assert_bits_equal(c, co, "float64 depth")
+    try:
+        import cv2
+    except ImportError:
+        return
+    # what the reference does: interpolate in float64, cast afterwards; then its own float32 pipeline
+    d64 = cv2.resize(dep, (120, 90), interpolation=cv2.INTER_LINEAR).astype(np.float32)
+    pr, _ = _oracle(img, d64, density="high")
+    assert np.allclose(p, pr, rtol=1e-5, atol=1e-5)
+
+
 def test_resized_tiled_scan_geometries(m):
     """Widths that are a multiple of 4 take the shared-memory tiled resize (up- and mild down-scaling);
     strong down-scaling falls back to the direct kernel.  Non-finite values sit on corners and edges."""
