@@ -9,7 +9,7 @@ The package holds only what that path needs: ``csrc/`` (CUDA kernels + the C ABI
 """
 from .api import create_depth_preview, depth_preview_bgr, depth_to_point_cloud, depth_to_point_cloud_batch
 from .engine import DENSITY_STEP, BatchStream, EmitResult, FrameEngine, reference_intrinsics, shard_frames
-from .hostpipe import HostFramePipeline
+from .hostpipe import HostFramePipeline, MultiGpuPipeline
 from ._lib import D2pcConfig, D2pcError, D2pcFrameParams, load_library
 from .pipeline import point_cloud_stage
 from .refine import refine_point_cloud, statistical_outlier_removal
@@ -17,7 +17,7 @@ from .writers import (las_point_records, ply_vertex_records, preview_lists, prev
                       save_point_cloud, save_xyz, xyz_text)
 
 __all__ = [
-    "depth_to_point_cloud", "depth_to_point_cloud_batch", "create_depth_preview", "depth_preview_bgr", "FrameEngine", "HostFramePipeline",
+    "depth_to_point_cloud", "depth_to_point_cloud_batch", "create_depth_preview", "depth_preview_bgr", "FrameEngine", "HostFramePipeline", "MultiGpuPipeline",
     "EmitResult", "BatchStream", "DENSITY_STEP", "reference_intrinsics", "shard_frames",
     "D2pcConfig", "D2pcFrameParams", "D2pcError", "load_library",
     "preview_rows", "preview_lists", "xyz_text", "save_xyz", "las_point_records", "save_las", "ply_vertex_records",

@@ -23,6 +23,7 @@
 //            larger than the distance to everything unvisited, which makes the result exact
 //   stats    deterministic two-pass reduction -> threshold
 //   compact  per-tile kept counts, scan, ordered copy of kept rows + their source indices
+#include <stdlib.h>
 #include "d2pc_device.cuh"
 
 namespace d2pc {
@@ -216,13 +217,13 @@ __global__ void __launch_bounds__(kSorThreads) sor_trial_kernel(SorWs w, const f
   if (threadIdx.x == 0 && s_new) atomicAdd(&h->trial_occ[trial], s_new);
 }
 
-__global__ void sor_choose_kernel(SorWs w) {
+__global__ void sor_choose_kernel(SorWs w, double target_occ) {
   if (threadIdx.x != 0) return;
   SorHeader *h = w.hdr;
   int best = 0;
   for (int t = 0; t < kSorTrials; ++t) {
     const double occ = h->trial_occ[t] ? (double)h->n / (double)h->trial_occ[t] : 0.0;
-    if (occ >= kSorTargetOcc) best = t;  // finest size that still fills its cells
+    if (occ >= target_occ) best = t;  // finest size that still fills its cells
   }
   h->chosen = (uint32_t)best;
   h->h = h->trial_h[best];
@@ -698,7 +699,8 @@ extern "C" int d2pc_sor_enqueue(const float *d_xyz, const float *d_rgb, const ui
     sor_trial_kernel<<<stride_blocks, kSorThreads, 0, st>>>(w, d_xyz, t);
     D2PC_CHECK_LAUNCH();
   }
-  sor_choose_kernel<<<1, 32, 0, st>>>(w);
+  const char *occ_env = getenv("D2PC_SOR_OCC");  // measurement aid
+  sor_choose_kernel<<<1, 32, 0, st>>>(w, occ_env ? atof(occ_env) : kSorTargetOcc);
   D2PC_CHECK_LAUNCH();
   sor_clear_kernel<<<148 * 8, 256, 0, st>>>(w);
   D2PC_CHECK_LAUNCH();

@@ -46,12 +46,30 @@ def bench(iters=5, cpu=True):
             for _ in range(2):   # allocator and first-launch warm-up
                 m.statistical_outlier_removal(xyz, rgb, return_device=True)
             torch.cuda.synchronize()
-            a.record()
+            per_call = []
             for _ in range(iters):
+                a.record()
                 p, c, idx, st = m.statistical_outlier_removal(xyz, rgb, return_device=True)
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / iters
+                b.record()
+                torch.cuda.synchronize()
+                per_call.append(a.elapsed_time(b))
+            ms = sorted(per_call)[len(per_call) // 2]   # median: a call is one synchronous request
+            if os.environ.get("PER_CALL"):
+                print(name, kind, ["%.2f" % x for x in per_call], file=sys.stderr)
+            if os.environ.get("TIMELINE"):   # where a call's time goes (CUPTI through torch.profiler)
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    m.statistical_outlier_removal(xyz, rgb, return_device=True)
+                    torch.cuda.synchronize()
+                prof.export_chrome_trace("/tmp/_sorb.json")
+                ev = sorted((e for e in json.load(open("/tmp/_sorb.json"))["traceEvents"] if e.get("cat") == "kernel"),
+                            key=lambda e: e["ts"])
+                tot = {}
+                for e in ev:
+                    nm = e["name"].split("(")[0].replace("void d2pc::", "").replace("d2pc::", "")[:32]
+                    tot[nm] = tot.get(nm, 0.0) + e["dur"]
+                print(name, kind, "%.2f ms timed; profiled call span %.0f us: " % (ms, ev[-1]["ts"] + ev[-1]["dur"] - ev[0]["ts"]) +
+                      ", ".join("%s %.0f" % kv for kv in sorted(tot.items(), key=lambda kv: -kv[1])[:5]), file=sys.stderr)
             row = {"points": int(xyz.shape[0]), "kept": int(p.shape[0]), "ms": round(ms, 3),
                    "mpoints_per_s": round(xyz.shape[0] / ms / 1e3, 1)}
             if cpu and name != "1080p_high" or (cpu and kind == "scene"):

@@ -76,3 +76,47 @@ def test_two_rank_frame_sharding(tmp_path):
         p, _ = O.depth_to_point_cloud(cases.make_image(12, 16, 1000 + i), cases.make_depth(12, 16, 1000 + i, "uniform"),
                                       density="high")
         assert flat[i] == float(p[:, 2].astype(np.float64).sum())
+
+
+def test_multi_gpu_pipeline_orchestration_on_cpu():
+    """MultiGpuPipeline's host logic without a GPU: per-device pipelines are stand-ins that record what they are
+    asked to do; every frame is processed exactly once, on the device shard_frames assigns, concurrently, and an
+    exception in one shard reaches the caller."""
+    import threading
+    sys.path.insert(0, ROOT)
+    from image_to_pointcloud_b200.engine import shard_frames
+    from image_to_pointcloud_b200.hostpipe import MultiGpuPipeline
+
+    seen = {}
+    barrier = threading.Barrier(3, timeout=20)
+
+    class Fake:
+        def __init__(self, d):
+            self.d = d
+
+        def alloc_pinned_inputs(self, n):
+            return None, torch.zeros((n, 2, 2))
+
+        def alloc_pinned_outputs(self, n):
+            return torch.zeros((n, 4, 3)), torch.zeros((n, 4, 3)), torch.zeros(n, dtype=torch.int32)
+
+        def run_pinned(self, images, depths, xyz, rgb, counts):
+            barrier.wait()   # all three shards are in flight at the same time
+            seen[self.d] = depths[:, 0, 0].tolist()
+            xyz[:] = depths[:, :1, :1] + 100.0
+            counts[:] = 4
+            if self.d == "boom":
+                raise ValueError("shard failed")
+
+    n = 10
+    pipe = MultiGpuPipeline(2, 2, devices=[0, 1, 2], pipeline_factory=Fake)
+    depths = torch.arange(n, dtype=torch.float32).reshape(n, 1, 1).expand(n, 2, 2).contiguous()
+    xyz, rgb, counts = pipe.alloc_pinned_outputs(n)
+    pipe.run_pinned(None, depths, xyz, rgb, counts)
+    for r in range(3):
+        assert seen[r] == [float(i) for i in shard_frames(n, 3, r)]
+    assert xyz[:, 0, 0].tolist() == [100.0 + i for i in range(n)] and counts.tolist() == [4] * n
+    barrier.reset()
+    bad = MultiGpuPipeline(2, 2, devices=[0, "boom", 2], pipeline_factory=Fake)
+    with pytest.raises(ValueError):
+        bad.run_pinned(None, depths, xyz, rgb, counts)

@@ -364,6 +364,27 @@ def test_host_pipeline_matches_single_calls(m):
         assert_bits_equal(outs[i][0], po[keep], f"masked frame {i}")
 
 
+def test_multi_gpu_pipeline_shards_frames(m):
+    """MultiGpuPipeline: one host thread per device pipeline, frames sharded by frame, no collective.  On a
+    one-GPU box two pipelines on the same device exercise the same threading; with more GPUs every device runs."""
+    import torch
+    rng = np.random.default_rng(41)
+    H, W, h, w, n = 96, 128, 41, 57, 13
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(n)]
+    deps = [(rng.random((h, w)) * (3 + i)).astype(np.float32) for i in range(n)]
+    deps[5][2, 2] = np.nan   # one frame through the exact fallback
+    devs = list(range(torch.cuda.device_count()))
+    for devices in ([0, 0], devs if len(devs) > 1 else [0]):
+        pipe = m.MultiGpuPipeline(H, W, h, w, devices=devices, chunk=4, density="medium")
+        assert [len(r) for r in pipe.shards(n)] == [len(m.shard_frames(n, len(devices), r)) for r in range(len(devices))]
+        outs = pipe.run(imgs, deps)
+        assert len(outs) == n
+        for i in range(n):
+            po, co = _oracle(imgs[i], deps[i], density="medium")
+            assert_bits_equal(outs[i][0], po, f"frame {i} on {devices}")
+            assert_bits_equal(outs[i][1], co, f"frame {i} on {devices}")
+
+
 def test_4k_full_size_properties_and_oracle(m):
     """BASELINE config 3 size: full compare against the oracle plus size-independent properties."""
     img, dep, kw = cases.build_case(cases.LARGE_CASES["c3_4k_dav2"])
