@@ -217,6 +217,34 @@ def test_percentile_selection_on_hard_distributions(m):
         assert_bits_equal(res.xyz[0].cpu().numpy(), po, name)
 
 
+def test_cooperative_selection_equals_single_cta_selection(m, monkeypatch):
+    """The K-CTA two-launch selection (small batches, 4K frames) against the one-CTA-per-bracket kernel and the
+    oracle: p2 / p98 float64 bit-equal for every K, on batches of 3 and 5 frames (batches of 1 or 2 take the
+    index-ordered kernel) with hard distributions and a frame that needs the fallback."""
+    rng = np.random.default_rng(52)
+    H, W = 270, 480
+    deps = [
+        (rng.random((H, W)) * 20).astype(np.float32),
+        np.maximum(rng.standard_normal((H, W)) - 0.5, 0).astype(np.float32),      # 30% exact zeros
+        np.round(rng.random((H, W)) * 50).astype(np.float32),                      # heavy ties
+        (10 + rng.random((H, W)) * 1e-3).astype(np.float32),                       # narrow key range
+        np.exp(rng.standard_normal((H, W)) * 4).astype(np.float32),
+    ]
+    deps[4][11, 13] = np.nan                                                        # exact fallback
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in deps]
+    want = [O.depth_to_point_cloud(i, d, density="low", return_info=True) for i, d in zip(imgs, deps)]
+    for nb in (3, 5):
+        for K in ("0", "2", "3", "8", "64"):
+            monkeypatch.setenv("D2PC_SELECT_COOP", K)
+            eng, cfg, res = _engine_run(m, imgs[:nb], deps[:nb], density="low")
+            prm = eng.frame_params(cfg)
+            for b in range(nb):
+                po, co, info = want[b]
+                assert np.float64(prm[b]["p2"]).tobytes() == np.float64(info["p2"]).tobytes(), (nb, K, b)
+                assert np.float64(prm[b]["p98"]).tobytes() == np.float64(info["p98"]).tobytes(), (nb, K, b)
+                assert_bits_equal(res.xyz[b].cpu().numpy(), po, f"nb={nb} K={K} frame {b}")
+
+
 def test_range_mask_and_compaction(m):
     rng = np.random.default_rng(35)
     for (H, W, h, w) in [(96, 160, 96, 160), (121, 161, 77, 91), (300, 500, 300, 500)]:
