@@ -58,39 +58,38 @@ __global__ void __launch_bounds__(32) mask_prepare_kernel(KParams kp, EmitArgs e
 // lane, a warp reduction, no shared memory, no barrier.  Mode-0 frames evaluate the exact chain.
 constexpr int kCountWarps = 8;
 template <int STEP>
-__global__ void __launch_bounds__(kCountWarps * 32) mask_count_kernel(KParams kp, EmitArgs ea, uint32_t tiles_per_frame,
+__global__ void __launch_bounds__(kCountWarps * 32, 6) mask_count_kernel(KParams kp, EmitArgs ea, uint32_t tiles_per_frame,
                                                                      uint32_t total_tiles, unsigned long long magic_w) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t t = blockIdx.x * (uint32_t)kCountWarps + (uint32_t)warp;
   if (t >= total_tiles) return;
   const uint32_t b = t / tiles_per_frame, tile = t - b * tiles_per_frame;
   const FrameState *fs = kp.state + b;
-  if (fs->status != D2PC_FRAME_READY) return;
   const uint32_t N = kp.g.N, W = (uint32_t)kp.g.W, NU = (uint32_t)kp.g.nu;
   const uint32_t tile_base = tile * (uint32_t)kEmitTile;
   const float *frame = kp.depth + (size_t)b * kp.g.P;
-  float4 r[8];   // the four sampled depths of each of the lane's 8 row groups (same pixels as emit_fast_tile)
+  const int32_t status = fs->status;   // looked at after the tile's loads have been issued
+  // the four sampled depths of row group j (same pixels as emit_fast_tile)
+  auto load_group = [&](int j, bool *ok) -> float4 {
+    const uint32_t p0 = tile_base + 4u * (uint32_t)(j * 32 + lane);
+    *ok = p0 < N;  // N % 4 == 0 on this path
+    if (!*ok) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (STEP == 1) return ldg_stream_f4(frame + p0);
+    const uint32_t jv = (uint32_t)(((unsigned long long)p0 * magic_w) >> 40), ju = p0 - jv * NU;
+    const float *src = frame + (size_t)(jv * (uint32_t)STEP) * W + ju * (uint32_t)STEP;
+    if (STEP == 2) {
+      const float4 da = ldg_stream_f4(src), db = ldg_stream_f4(src + 4);
+      return make_float4(da.x, da.z, db.x, db.z);
+    }
+    return make_float4(__ldg(src), __ldg(src + 4), __ldg(src + 8), __ldg(src + 12));
+  };
+  float4 r[8];
   bool ok[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t p0 = tile_base + 4u * (uint32_t)(j * 32 + lane);
-    ok[j] = p0 < N;  // N % 4 == 0 on this path
-    if (!ok[j]) continue;
-    if (STEP == 1) {
-      r[j] = ldg_stream_f4(frame + p0);
-    } else {
-      const uint32_t jv = (uint32_t)(((unsigned long long)p0 * magic_w) >> 40), ju = p0 - jv * NU;
-      const float *src = frame + (size_t)(jv * (uint32_t)STEP) * W + ju * (uint32_t)STEP;
-      if (STEP == 2) {
-        const float4 da = ldg_stream_f4(src), db = ldg_stream_f4(src + 4);
-        r[j] = make_float4(da.x, da.z, db.x, db.z);
-      } else {
-        r[j] = make_float4(__ldg(src), __ldg(src + 4), __ldg(src + 8), __ldg(src + 12));
-      }
-    }
-  }
+  for (int j = 0; j < 8; ++j) r[j] = load_group(j, &ok[j]);
   uint32_t cnt = 0;
   const MaskParams mp = load_mask(fs);
+  if (status != D2PC_FRAME_READY) return;   // uniform per warp
   const bool by_depth = !ea.use_z || mp.mode == 1;
   if (by_depth) {
 #pragma unroll
@@ -101,17 +100,20 @@ __global__ void __launch_bounds__(kCountWarps * 32) mask_count_kernel(KParams kp
         cnt += mask_keep(r[j].z, 0.0f, mp, ea) ? 1u : 0u;
         cnt += mask_keep(r[j].w, 0.0f, mp, ea) ? 1u : 0u;
       }
-  } else {
+  } else {  // rare: a rolled loop that loads again (L1 / L2 hits) -- indexing r[] dynamically would put it in local memory
     const NormParams np_ = fs->norm;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j)
-      if (ok[j]) {
-        const float raw[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-        for (int k = 0; k < 4; ++k) {
-          const double n = normalised_depth(raw[k], np_, ea.pc.invert);
-          cnt += mask_keep(raw[k], (float)(n * ea.pc.scale), mp, ea) ? 1u : 0u;
-        }
+    for (int j = 0; j < 8; ++j) {
+      bool okj;
+      const float4 q = load_group(j, &okj);
+      if (!okj) continue;
+      const float raw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // same expression as back_project's z
+        const double n = normalised_depth(raw[k], np_, ea.pc.invert);
+        cnt += mask_keep(raw[k], (float)(n * ea.pc.scale), mp, ea) ? 1u : 0u;
       }
+    }
   }
   cnt = warp_sum(cnt);
   if (lane == 0) kp.tile_state[(size_t)b * tiles_per_frame + tile] = (unsigned long long)cnt;

@@ -109,14 +109,18 @@ __device__ __forceinline__ MaskParams load_mask(const FrameState *fs) {
   m.mode = fs->mask_mode; m.lo = fs->mask_lo; m.hi = fs->mask_hi;
   return m;
 }
-__device__ __forceinline__ bool mask_keep(float raw, float z32, const MaskParams &m, const EmitArgs &ea) {
+__device__ __forceinline__ bool mask_keep_v(float raw, float z32, const MaskParams &m, int32_t use_z, int32_t drop_nf,
+                                            float z_min, float z_max) {
   bool kk = true;
-  if (ea.use_z) {
+  if (use_z) {
     if (m.mode == 1) kk = (raw >= m.lo) && (raw <= m.hi);
-    else kk = (z32 >= ea.z_min) && (z32 <= ea.z_max);
+    else kk = (z32 >= z_min) && (z32 <= z_max);
   }
-  if (ea.drop_nf && !is_finite_f32(raw)) kk = false;
+  if (drop_nf && !is_finite_f32(raw)) kk = false;
   return kk;
+}
+__device__ __forceinline__ bool mask_keep(float raw, float z32, const MaskParams &m, const EmitArgs &ea) {
+  return mask_keep_v(raw, z32, m, ea.use_z, ea.drop_nf, ea.z_min, ea.z_max);
 }
 
 // mask_interval (d2pc_math.h) by one warp: 32 probes of the ordered key space per round instead of
