@@ -121,7 +121,7 @@ def depth_to_point_cloud(image: np.ndarray, depth: np.ndarray,
         check_depth_dtype(depth, int(img_h), int(img_w))
         if smooth and len(smoothing_kernel(smooth_ksize)) > MAX_SMOOTH_KSIZE:
             # the reference accepts any size (cv2.GaussianBlur); this build keeps the coefficients in kernel
-            # arguments and stops at 31 -- refused before any GPU work (the reference's only caller uses 5)
+            # arguments and stops at 255 taps -- refused before any GPU work (the reference's only caller uses 5)
             raise ValueError(f"smooth_ksize {smooth_ksize} gives a kernel larger than {MAX_SMOOTH_KSIZE}")
         img_c = _image_channels(image)
         eng = _engine_for(int(img_h), int(img_w), img_c, int(dep_h), int(dep_w), device)

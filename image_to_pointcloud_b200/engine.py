@@ -40,7 +40,7 @@ _SMALL_GAUSSIAN = {  # cv2.getGaussianKernel(k, 0, CV_64F): fixed tables for k <
     7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
     9: [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256],
 }
-MAX_SMOOTH_KSIZE = 31
+MAX_SMOOTH_KSIZE = 255
 
 
 def smoothing_kernel(smooth_ksize) -> list:

@@ -183,7 +183,7 @@ int d2pc_path_trace_offset(const D2pcConfig *cfg, size_t *offset);
  * Arithmetic follows OpenCV 4.13's float64 separable filter (rows with FMA in the vector body and
  * plain multiply-add in the last W%4 columns, then symmetric column sums; BORDER_REFLECT_101), so
  * percentile-branch frames are bit-exact for k <= 9; the float32 (min/max) branch is within 1e-6. */
-#define D2PC_MAX_SMOOTH_KSIZE 31
+#define D2PC_MAX_SMOOTH_KSIZE 255
 int d2pc_smooth_scratch_bytes(const D2pcConfig *cfg, size_t *bytes);
 int d2pc_emit_smooth_enqueue(const D2pcConfig *cfg, const float *d_depth, const uint8_t *d_bgr,
                              void *d_workspace, size_t workspace_bytes, int32_t ksize,

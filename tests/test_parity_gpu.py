@@ -341,6 +341,23 @@ def test_smoothing_larger_frames(m):
         assert_bits_equal(p, po[keep], "smooth + mask")
 
 
+def test_smoothing_with_large_kernels(m):
+    """a6 with kernels far beyond the caller's default 5 (the reference accepts any size, app.py:209-212): up to
+    255 taps, larger than the image (REFLECT_101 wraps repeatedly).  Coefficients for k > 7 come from exp(): within
+    the 1e-5 tolerance of the oracle (which equals cv2.GaussianBlur to 1e-15), not bit-pinned."""
+    rng = np.random.default_rng(53)
+    H, W = 70, 90
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    dep = (rng.random((H, W)) * 20).astype(np.float32)
+    for k in (33, 63, 255):
+        po, co = _oracle(img, dep, density="medium", smooth=True, smooth_ksize=k)
+        p, c = m.depth_to_point_cloud(img, dep, density="medium", smooth=True, smooth_ksize=k)
+        assert p.shape == po.shape and np.array_equal(c, co)
+        np.testing.assert_allclose(p, po, rtol=1e-5, atol=1e-6, err_msg=f"k={k}")
+    with pytest.raises(ValueError):   # beyond the coefficient table: refused before any GPU work
+        m.depth_to_point_cloud(img, dep, smooth=True, smooth_ksize=257)
+
+
 def test_bounds_equal_numpy_minmax(m):
     """f4: the bounds fused into emit equal points[:, k].min()/max() (generate_gis_metadata, app.py:393-400)."""
     rng = np.random.default_rng(39)
