@@ -28,3 +28,13 @@ for _ in range(iters):
     vx, vr, vi, vc = eng.voxel_downsample(cfg, res, vs, check_error=False)
 torch.cuda.synchronize()
 print(name, vs, "points", int(cnt[0]), "voxels", int(vc[0]))
+if os.environ.get("TIMELINE"):
+    import json
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        eng.voxel_downsample(cfg, res, vs, check_error=False)
+        torch.cuda.synchronize()
+    prof.export_chrome_trace("/tmp/_vox.json")
+    ev = sorted((e for e in json.load(open("/tmp/_vox.json"))["traceEvents"] if e.get("cat") == "kernel"), key=lambda e: e["ts"])
+    for e in ev:
+        print("  %9.1f %8.1f  %-40s %s" % (e["ts"] - ev[0]["ts"], e["dur"], e["name"].split("(")[0].replace("d2pc::", "")[:40], e["args"].get("grid")))

@@ -65,3 +65,25 @@ def test_c1_480p(ref):
     from tests import cases
     img, dep, kw = cases.build_case(cases.LARGE_CASES["c1_480p_medium"])
     _cmp(ref, img, dep, **kw)
+
+
+def test_drop_in_signature_equals_the_reference_signature(ref):
+    """The drop-in's positional parameters, their order, kinds and defaults are the reference's own
+    (backend/app.py:174-180), compared with inspect on the loaded reference function; everything the drop-in adds
+    is keyword-only.  The same for the other rebindable functions."""
+    import inspect
+
+    import image_to_pointcloud_b200 as m
+    from oracle import ref_loader
+    rs, ms = inspect.signature(ref), inspect.signature(m.depth_to_point_cloud)
+    rp, mp = list(rs.parameters.values()), list(ms.parameters.values())
+    assert [(p.name, p.kind, p.default) for p in mp[:len(rp)]] == [(p.name, p.kind, p.default) for p in rp]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in mp[len(rp):])
+    app = ref_loader.load_reference_module() if hasattr(ref_loader, "load_reference_module") else None
+    if app is not None:
+        for name in ("create_depth_preview", "refine_point_cloud", "save_point_cloud", "save_xyz", "save_las", "save_ply"):
+            r = list(inspect.signature(getattr(app, name)).parameters.values())
+            g = list(inspect.signature(getattr(m, name)).parameters.values())
+            assert [(p.name, p.default) for p in g[:len(r)]] == [(p.name, p.default) for p in r], name
+            assert all(p.default is not inspect.Parameter.empty or p.kind is inspect.Parameter.KEYWORD_ONLY
+                       for p in g[len(r):]), name
