@@ -40,7 +40,8 @@ out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400, comman
 for (k, g), v in agg.items():
     out.append(f"{k:80s} grid {g:18s} launches {len(v):3d}  mean {sum(v) / len(v):9.1f} us")
 step = [(k, g, sum(v) / len(v)) for (k, g), v in agg.items()
-        if g in ("(128, 1, 1)", "(254, 128, 1)", "(2, 128, 1)", "(259200, 1, 1)", "(1, 1, 1)") and "FillFunctor" not in k]
+        if (g in ("(128, 1, 1)", "(254, 128, 1)", "(2, 128, 1)", "(259200, 1, 1)", "(1, 1, 1)") or
+            ("scan_native" in k and g.endswith(", 128, 1)"))) and "FillFunctor" not in k]
 tot = sum(x[2] for x in step)
 out += ["", "one batch-128 step = sample + scan + select + status + emit = %.1f us; shares:" % tot]
 out += [f"  {k.split('(')[0][:40]:42s} {t:8.1f} us  {100 * t / tot:5.1f} %" for k, g, t in step]

@@ -8,6 +8,6 @@ timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras >
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${P}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > ${P}_ncu1.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on \
-    -k regex:"sample_kernel|scan_native_kernel|select_kernel|emit_fast_kernel" -s 12 -c 8 -o ${P}_prof \
+    -k regex:"sample_kernel|scan_native|select_kernel|emit_fast_kernel" -s 12 -c 8 -o ${P}_prof \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > ${P}_ncu2.log 2>&1
 tail -c 600 ${P}_bench_default.json

@@ -245,6 +245,37 @@ def test_cooperative_selection_equals_single_cta_selection(m, monkeypatch):
                 assert_bits_equal(res.xyz[b].cpu().numpy(), po, f"nb={nb} K={K} frame {b}")
 
 
+def test_multi_tile_scan_equals_single_tile_scan(m, monkeypatch):
+    """The scan kernel that walks several tiles per CTA (large grids; forced here with D2PC_SCAN_TPC) against the
+    oracle: frames whose last tile is partial, tile counts that leave a CTA with fewer tiles than TPC, clustered
+    tiles (every pixel of a tile deferred), a frame for the fallback."""
+    rng = np.random.default_rng(54)
+
+    def frames(H, W):
+        deps = [
+            (rng.random((H, W)) * 20).astype(np.float32),
+            np.sort((rng.random(H * W) * 20).astype(np.float32)).reshape(H, W),   # extremes clustered in whole tiles
+            np.round(rng.random((H, W)) * 50).astype(np.float32),
+            (rng.random((H, W)) * 20).astype(np.float32),
+        ]
+        deps[3][H // 2, W // 2] = np.inf
+        imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in deps]
+        want = [O.depth_to_point_cloud(i, d, density="medium", return_info=True) for i, d in zip(imgs, deps)]
+        return imgs, deps, want
+
+    # 203 x 517 = 104 951 pixels: 12 full tiles + a partial one, unaligned rows; 256 x 512: 16 full tiles
+    cases_ = [frames(203, 517), frames(256, 512)]
+    for tpc in ("1", "2", "4"):
+        monkeypatch.setenv("D2PC_SCAN_TPC", tpc)
+        for imgs, deps, want in cases_:
+            eng, cfg, res = _engine_run(m, imgs, deps, density="medium")
+            prm = eng.frame_params(cfg)
+            for b, (po, co, info) in enumerate(want):
+                assert np.float64(prm[b]["p2"]).tobytes() == np.float64(info["p2"]).tobytes(), (tpc, deps[0].shape, b)
+                assert np.float64(prm[b]["p98"]).tobytes() == np.float64(info["p98"]).tobytes(), (tpc, deps[0].shape, b)
+                assert_bits_equal(res.xyz[b].cpu().numpy(), po, f"tpc={tpc} {deps[0].shape} frame {b}")
+
+
 def test_range_mask_and_compaction(m):
     rng = np.random.default_rng(35)
     for (H, W, h, w) in [(96, 160, 96, 160), (121, 161, 77, 91), (300, 500, 300, 500)]:
