@@ -27,6 +27,8 @@
 //     (CTA scan + one atomic per CTA; the order of the output rows is unspecified, as in Open3D).
 // Against the first design (64-byte hash entries, 1 GB table for a 4K frame, every access a random DRAM
 // read-modify-write) the random traffic drops to 4-byte entries in an L2-resident table.
+#include <stdlib.h>
+
 #include "d2pc_device.cuh"
 
 namespace d2pc {
@@ -128,9 +130,26 @@ __global__ void __launch_bounds__(256) vox_clear_kernel(VoxTable t, const uint32
   const uint32_t cap4 = (t.hdr->frame_cap + 3u) / 4u, fl16 = (*count + 15u) / 16u;
   uint4 *s4 = reinterpret_cast<uint4 *>(t.slots), *f4 = reinterpret_cast<uint4 *>(t.flags);
   const uint32_t stride = gridDim.x * blockDim.x;
+  const uint64_t pol_keep = l2_policy(false, true);   // the slots should still be in L2 when the claims arrive
+  const float e = __uint_as_float(kVoxEmptySlot);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap4; i += stride)
-    s4[i] = make_uint4(kVoxEmptySlot, kVoxEmptySlot, kVoxEmptySlot, kVoxEmptySlot);
+    stg_f4_pol(reinterpret_cast<float *>(s4 + i), make_float4(e, e, e, e), pol_keep);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fl16; i += stride) f4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// L2 residency: the 4-byte slot table (66 MB for a 4K frame) is what is probed at random and must stay in the
+// 126 MB L2; the keys and accumulators (8 + 40 bytes per row) stream through and would push it out (ncu: 70% of the
+// claim kernel's CAS sectors missed L2).  Slots are cleared evict-last, streamed arrays are touched evict-first.
+__device__ __forceinline__ void red_add_u64_pol(unsigned long long *p, unsigned long long v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_u64_pol(const unsigned long long *p, uint64_t pol) {
+  unsigned long long v;
+  asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_u64_pol(unsigned long long *p, unsigned long long v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(pol) : "memory");
 }
 
 struct VoxRun {
@@ -149,10 +168,11 @@ __device__ __forceinline__ unsigned long long ld_key(const unsigned long long *p
   return v;
 }
 
-__device__ __forceinline__ void vox_publish(const VoxTable &t, const VoxRun &r, uint32_t row) {
+__device__ __forceinline__ void vox_publish(const VoxTable &t, const VoxRun &r, uint32_t row, uint64_t pol) {
   unsigned long long *a = t.acc + 5 * (size_t)row;
-  a[0] = r.cnt_r; a[1] = r.g_b; a[2] = r.sx; a[3] = r.sy; a[4] = r.sz;
-  t.keys[row] = r.key;
+  st_u64_pol(a + 0, r.cnt_r, pol); st_u64_pol(a + 1, r.g_b, pol); st_u64_pol(a + 2, r.sx, pol);
+  st_u64_pol(a + 3, r.sy, pol); st_u64_pol(a + 4, r.sz, pol);
+  st_u64_pol(t.keys + row, r.key, pol);
 }
 __device__ __forceinline__ void vox_add(const VoxTable &t, const VoxRun &r, uint32_t rep) {
   unsigned long long *a = t.acc + 5 * (size_t)rep;
@@ -172,6 +192,7 @@ __device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap,
                                           const uint32_t (&row)[NR], const bool (&act)[NR]) {
   uint32_t slot[NR], fp[NR], e[NR];
   bool todo[NR];
+  const uint64_t pol_stream = l2_policy(true, false);
 #pragma unroll
   for (int h = 0; h < NR; ++h) {
     const unsigned long long hh = hash_u64(key[h]);
@@ -186,7 +207,7 @@ __device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap,
     if (!any) break;
 #pragma unroll
     for (int h = 0; h < NR; ++h)
-      if (todo[h]) e[h] = atomicCAS(t.slots + slot[h], kVoxEmptySlot, fp[h] | row[h]);
+      if (todo[h]) e[h] = atomicCAS(t.slots + slot[h], kVoxEmptySlot, fp[h] | row[h]);   // (atom.cas takes no cache hint)
     unsigned long long k[NR];
     bool cmp[NR];
 #pragma unroll
@@ -198,7 +219,7 @@ __device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap,
         todo[h] = false;
       } else if ((e[h] & 0xFF000000u) == fp[h]) {
         cmp[h] = true;
-        k[h] = ld_key(t.keys + (e[h] & 0x00FFFFFFu));
+        k[h] = ld_u64_pol(t.keys + (e[h] & 0x00FFFFFFu), pol_stream);
       }
     }
 #pragma unroll
@@ -209,9 +230,9 @@ __device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap,
         unsigned long long *a = t.acc + 5 * (size_t)(e[h] & 0x00FFFFFFu);
         unsigned long long v[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) v[c] = __ldcg(mine + c);
+        for (int c = 0; c < 5; ++c) v[c] = ld_u64_pol(mine + c, pol_stream);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) atomicAdd(a + c, v[c]);
+        for (int c = 0; c < 5; ++c) red_add_u64_pol(a + c, v[c], pol_stream);
         todo[h] = false;
       } else {
         slot[h] = slot[h] + 1u == frame_cap ? 0u : slot[h] + 1u;
@@ -227,6 +248,7 @@ __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, 
 // One row per lane, kVoxPerThread consecutive 32-row groups per warp.  Rows of a group that share a
 // voxel with their left neighbour form a run; a segmented warp scan sums each run into its last
 // lane, which alone touches the table.  Every lane has one independent probe in flight.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, const float *xyz, const float *rgb,
                                                                     const uint32_t *count, double vs, int32_t *err) {
   const uint32_t M = *count;
@@ -238,6 +260,7 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double lim = (double)(1 << kVoxBits);
   const double inv_vs = 1.0 / vs;
+  const uint64_t pol_stream = l2_policy(true, false);
   unsigned long long keys[kVoxPerThread];
   uint32_t rows[kVoxPerThread];
   bool act[kVoxPerThread];
@@ -252,9 +275,11 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
       const float x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2);
       const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
       const double o0 = (double)x0 - vmin0, o1 = (double)x1 - vmin1, o2 = (double)x2 - vmin2;
-      // floor((p - vmin) / vs): correctly rounded quotient from the reciprocal (d2pc_math.h div_by_const)
-      const double i0d = floor(div_by_const(o0, vs, inv_vs)), i1d = floor(div_by_const(o1, vs, inv_vs)),
-                   i2d = floor(div_by_const(o2, vs, inv_vs));
+      // floor((p - vmin) / vs): correctly rounded quotient from the reciprocal (d2pc_math.h).  The unguarded form is
+      // enough here: offsets are >= 0; a quotient so small that the residual steps underflow floors to 0 either way,
+      // and a non-finite offset gives NaN, which fails the range test below like the IEEE quotient (inf) would
+      const double i0d = floor(div_by_const_fast(o0, vs, inv_vs)), i1d = floor(div_by_const_fast(o1, vs, inv_vs)),
+                   i2d = floor(div_by_const_fast(o2, vs, inv_vs));
       if (i0d >= 0.0 && i0d < lim && i1d >= 0.0 && i1d < lim && i2d >= 0.0 && i2d < lim) {
         run.key = ((unsigned long long)i0d << (2 * kVoxBits)) | ((unsigned long long)i1d << kVoxBits) |
                   (unsigned long long)i2d;
@@ -284,9 +309,35 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
     keys[h] = run.key;
     rows[h] = i;
     act[h] = tail && run.key != kVoxNoKey;
-    if (act[h]) vox_publish(t, run, i);   // in row order: a streaming write
+    if (act[h]) vox_publish(t, run, i, pol_stream);   // in row order: a streaming write
+    else if (SPLIT && i < M) st_u64_pol(t.keys + i, kVoxNoKey, pol_stream);   // the claim kernel reads every row's key
   }
+  if (SPLIT) return;   // the table is touched by vox_claim_kernel (the kernel boundary orders the published sums)
   __threadfence();   // one fence for the lane's rows: sums and keys are in place before any row can be found
+  vox_claim<kVoxPerThread>(t, frame_cap, keys, rows, act);
+}
+
+// The table half of the insert as its own launch: the run leaders' keys come back from the keys array (a coalesced
+// read) and nothing of the row's arithmetic is alive, so the kernel needs few registers and twice as many probe
+// chains are in flight per SM -- the stage is a chain of L2 round trips (CAS -> key compare -> sums -> 5 RED per
+// member row), not a stream.
+__global__ void __launch_bounds__(kVoxThreads, 6) vox_claim_kernel(VoxTable t, const uint32_t *count) {
+  const uint32_t M = *count;
+  const uint32_t tile_base = blockIdx.x * (uint32_t)kVoxTile;
+  if (tile_base >= M || t.hdr->bad) return;
+  const uint32_t frame_cap = t.hdr->frame_cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long keys[kVoxPerThread];
+  uint32_t rows[kVoxPerThread];
+  bool act[kVoxPerThread];
+#pragma unroll
+  for (int h = 0; h < kVoxPerThread; ++h) {
+    const uint32_t i = tile_base + (uint32_t)((warp * kVoxPerThread + h) * 32 + lane);
+    rows[h] = i;
+    keys[h] = i < M ? __ldcs(t.keys + i) : kVoxNoKey;
+  }
+#pragma unroll
+  for (int h = 0; h < kVoxPerThread; ++h) act[h] = keys[h] != kVoxNoKey;
   vox_claim<kVoxPerThread>(t, frame_cap, keys, rows, act);
 }
 
@@ -340,14 +391,17 @@ __global__ void __launch_bounds__(kVoxThreads, 3) vox_extract_kernel(VoxTable t,
     for (int k = 0; k < 4; ++k) {
       if (!((f >> (8 * k)) & 1u)) continue;
       const unsigned long long cnt_r = w[k][0], g_b = w[k][1], sx = w[k][2], sy = w[k][3], sz = w[k][4], key = w[k][5];
-      const double n = (double)(uint32_t)(cnt_r >> 32);
+      const double n = (double)(uint32_t)(cnt_r >> 32);   // >= 1
+      // six means per row: one division (the reciprocal) and the correctly rounded quotients from it
+      // (div_by_const_fast: numerators are >= 0 and finite, n is a small integer -- same bits as a / n)
+      const double rn = 1.0 / n;
       float *ox = oxyz + 3 * (size_t)j, *oc = orgb + 3 * (size_t)j;
-      stg_stream_f1(ox + 0, (float)(vmin0 + ((double)(long long)sx * inv_scale) / n));
-      stg_stream_f1(ox + 1, (float)(vmin1 + ((double)(long long)sy * inv_scale) / n));
-      stg_stream_f1(ox + 2, (float)(vmin2 + ((double)(long long)sz * inv_scale) / n));
-      stg_stream_f1(oc + 0, (float)((double)(uint32_t)cnt_r / n));
-      stg_stream_f1(oc + 1, (float)((double)(uint32_t)(g_b >> 32) / n));
-      stg_stream_f1(oc + 2, (float)((double)(uint32_t)g_b / n));
+      stg_stream_f1(ox + 0, (float)(vmin0 + div_by_const_fast((double)(long long)sx * inv_scale, n, rn)));
+      stg_stream_f1(ox + 1, (float)(vmin1 + div_by_const_fast((double)(long long)sy * inv_scale, n, rn)));
+      stg_stream_f1(ox + 2, (float)(vmin2 + div_by_const_fast((double)(long long)sz * inv_scale, n, rn)));
+      stg_stream_f1(oc + 0, (float)div_by_const_fast((double)(uint32_t)cnt_r, n, rn));
+      stg_stream_f1(oc + 1, (float)div_by_const_fast((double)(uint32_t)(g_b >> 32), n, rn));
+      stg_stream_f1(oc + 2, (float)div_by_const_fast((double)(uint32_t)g_b, n, rn));
       if (oidx) {
         oidx[3 * (size_t)j + 0] = (int32_t)(key >> (2 * kVoxBits));
         oidx[3 * (size_t)j + 1] = (int32_t)((key >> kVoxBits) & ((1u << kVoxBits) - 1u));
@@ -420,8 +474,19 @@ extern "C" int d2pc_voxel_enqueue(const D2pcConfig *cfg, double voxel_size, cons
     D2PC_CHECK_LAUNCH();
     vox_clear_kernel<<<148 * 4, 256, 0, st>>>(t, d_count + b);
     D2PC_CHECK_LAUNCH();
-    vox_insert_kernel<<<tiles, kVoxThreads, 0, st>>>(t, d_xyz + ro, d_rgb + ro, d_count + b, voxel_size,
-                                                     d_vox_error + b);
+    // One fused insert kernel by default.  Publishing and claiming as two launches (the claim kernel then runs at
+    // 6 CTAs per SM instead of 4) was measured: 363 / 307 / 312 us against 338 / 294 / 266 us fused (4K frame, smooth
+    // scene 5 mm / uniform depth 5 mm / scene 5 cm) once the streamed arrays carry evict-first hints.
+    const char *se = getenv("D2PC_VOX_SPLIT");  // measurement aid: "1" = publish + claim as two launches
+    if (!(se && atoi(se) != 0)) {
+      vox_insert_kernel<false><<<tiles, kVoxThreads, 0, st>>>(t, d_xyz + ro, d_rgb + ro, d_count + b, voxel_size,
+                                                              d_vox_error + b);
+    } else {
+      vox_insert_kernel<true><<<tiles, kVoxThreads, 0, st>>>(t, d_xyz + ro, d_rgb + ro, d_count + b, voxel_size,
+                                                             d_vox_error + b);
+      D2PC_CHECK_LAUNCH();
+      vox_claim_kernel<<<tiles, kVoxThreads, 0, st>>>(t, d_count + b);
+    }
     D2PC_CHECK_LAUNCH();
     vox_extract_kernel<<<tiles, kVoxThreads, 0, st>>>(t, d_count + b, d_vox_xyz + ro, d_vox_rgb + ro,
                                                         d_vox_idx ? d_vox_idx + ro : nullptr, d_vox_count + b,
