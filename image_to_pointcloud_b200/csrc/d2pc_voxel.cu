@@ -187,9 +187,12 @@ __device__ __forceinline__ void vox_add(const VoxTable &t, const VoxRun &r, uint
 // and fenced): claim each voxel's slot or add the run's sums to the representative that holds it.  The NR probe
 // chains are interleaved (claims together, key reads of fingerprint matches together), so a lane has NR
 // independent L2 round trips in flight.
+// s_sums (optional): the lane's own run sums as [NR][5][kVoxThreads] in shared memory (the fused insert kernel keeps
+// them there: a member row then needs no third round trip to fetch what it is about to add).
 template <int NR>
 __device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap, const unsigned long long (&key)[NR],
-                                          const uint32_t (&row)[NR], const bool (&act)[NR]) {
+                                          const uint32_t (&row)[NR], const bool (&act)[NR],
+                                          const unsigned long long *s_sums = nullptr) {
   uint32_t slot[NR], fp[NR], e[NR];
   bool todo[NR];
   const uint64_t pol_stream = l2_policy(true, false);
@@ -230,7 +233,8 @@ __device__ __forceinline__ void vox_claim(const VoxTable &t, uint32_t frame_cap,
         unsigned long long *a = t.acc + 5 * (size_t)(e[h] & 0x00FFFFFFu);
         unsigned long long v[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) v[c] = ld_u64_pol(mine + c, pol_stream);
+        for (int c = 0; c < 5; ++c)
+          v[c] = s_sums ? s_sums[(h * 5 + c) * kVoxThreads + threadIdx.x] : ld_u64_pol(mine + c, pol_stream);
 #pragma unroll
         for (int c = 0; c < 5; ++c) red_add_u64_pol(a + c, v[c], pol_stream);
         todo[h] = false;
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
   const double lim = (double)(1 << kVoxBits);
   const double inv_vs = 1.0 / vs;
   const uint64_t pol_stream = l2_policy(true, false);
+  __shared__ unsigned long long s_sums[SPLIT ? 1 : kVoxPerThread * 5 * kVoxThreads];   // 40 KB (fused kernel only)
   unsigned long long keys[kVoxPerThread];
   uint32_t rows[kVoxPerThread];
   bool act[kVoxPerThread];
@@ -309,12 +314,19 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
     keys[h] = run.key;
     rows[h] = i;
     act[h] = tail && run.key != kVoxNoKey;
-    if (act[h]) vox_publish(t, run, i, pol_stream);   // in row order: a streaming write
+    if (act[h]) {
+      vox_publish(t, run, i, pol_stream);   // in row order: a streaming write
+      if (!SPLIT) {
+        unsigned long long *m = s_sums + (size_t)(h * 5) * kVoxThreads + threadIdx.x;
+        m[0] = run.cnt_r; m[kVoxThreads] = run.g_b; m[2 * kVoxThreads] = run.sx; m[3 * kVoxThreads] = run.sy;
+        m[4 * kVoxThreads] = run.sz;
+      }
+    }
     else if (SPLIT && i < M) st_u64_pol(t.keys + i, kVoxNoKey, pol_stream);   // the claim kernel reads every row's key
   }
   if (SPLIT) return;   // the table is touched by vox_claim_kernel (the kernel boundary orders the published sums)
   __threadfence();   // one fence for the lane's rows: sums and keys are in place before any row can be found
-  vox_claim<kVoxPerThread>(t, frame_cap, keys, rows, act);
+  vox_claim<kVoxPerThread>(t, frame_cap, keys, rows, act, s_sums);
 }
 
 // The table half of the insert as its own launch: the run leaders' keys come back from the keys array (a coalesced
