@@ -392,7 +392,7 @@ __device__ __forceinline__ float sor_filter(double kth) {
   return __double2float_ru(kth) * 1.000001f;
 }
 
-// The k smallest squared distances of one query, ascending.  STRIDE 1: a per-thread local array; STRIDE
+// The k smallest squared distances of one query (a max-heap, see below).  STRIDE 1: a per-thread local array; STRIDE
 // kSorThreads: one column of a [k][kSorThreads] shared-memory array (k <= kSorSharedK) -- the insertion loop is a
 // chain of dependent loads and stores, and local memory competes with the candidate stream for L1.
 template <int STRIDE>
@@ -401,6 +401,45 @@ struct KBest {
   __device__ __forceinline__ double &operator[](int t) const { return p[t * STRIDE]; }
 };
 constexpr int kSorSharedK = 24;
+
+// The k smallest squared distances are kept as a binary MAX-HEAP (root = the current k-th distance).  A candidate
+// that beats the root replaces it with one sift-down: at most log2(k) steps, the same few for every lane -- the
+// sorted list this replaces shifted up to k entries per insertion, and a warp paid the longest lane's chain for
+// every candidate any of its lanes accepted.  The ascending order the mean needs comes from one heap sort at the end.
+template <class B>
+__device__ __forceinline__ void kbest_sift(const B &best, int size, double v) {
+  int pos = 0;
+  while (true) {
+    const int l = 2 * pos + 1;
+    if (l >= size) break;
+    const int r = l + 1;
+    const double vl = best[l], vr = r < size ? best[r] : -1.0;
+    const bool right = vr > vl;
+    const double vc = right ? vr : vl;
+    if (vc <= v) break;
+    best[pos] = vc;
+    pos = right ? r : l;
+  }
+  best[pos] = v;
+}
+template <class B>
+__device__ __forceinline__ void kbest_push(const B &best, int k, double d2, double &kth, float &thrf) {
+  kbest_sift(best, k, d2);
+  kth = best[0];
+  thrf = sor_filter(kth);
+}
+// heap -> ascending array (in place), then the sum of the square roots in ascending order
+template <class B>
+__device__ __forceinline__ double kbest_sorted_sqrt_sum(const B &best, int k) {
+  for (int m = k; m > 1; --m) {
+    const double top = best[0], last = best[m - 1];
+    best[m - 1] = top;
+    kbest_sift(best, m - 1, last);
+  }
+  double s = 0.0;
+  for (int t = 0; t < k; ++t) s += sqrt(best[t]);  // ascending order, like std::accumulate over nanoflann's result
+  return s;
+}
 
 // Candidates of one cell.  A float32 estimate of the squared distance (relative error < 4e-7) rejects most
 // candidates for a sixth of the cost; whatever passes the (conservative) filter is evaluated exactly.
@@ -445,11 +484,7 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
           d2 += dy * dy;
           d2 += dz * dz;
           if (d2 < kth) {
-            int t = k - 1;
-            while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
-            best[t] = d2;
-            kth = best[k - 1];
-            thrf = sor_filter(kth);
+            kbest_push(best, k, d2, kth, thrf);
           }
         }
       }
@@ -479,11 +514,7 @@ __device__ __forceinline__ void sor_visit_cell(const SorWs &w, uint32_t cell, co
       d2 += dy * dy;
       d2 += dz * dz;
       if (d2 < kth) {
-        int t = k - 1;
-        while (t > 0 && best[t - 1] > d2) { best[t] = best[t - 1]; --t; }
-        best[t] = d2;
-        kth = best[k - 1];
-        thrf = sor_filter(kth);
+        kbest_push(best, k, d2, kth, thrf);
       }
     }
   }
@@ -571,9 +602,7 @@ __global__ void __launch_bounds__(kSorThreads, 4) sor_query_kernel(SorWs w, int 
         for (int32_t a1 = yi0; a1 <= yi1; ++a1) sor_visit_key(w, sor_key(a0, a1, a2), q, qf, best, k, thrf, kth);
     }
   }
-  double s = 0.0;
-  for (int t = 0; t < k; ++t) s += sqrt(best[t]);  // ascending order, like std::accumulate over nanoflann's result
-  w.avg[i] = s / (double)k;
+  w.avg[i] = kbest_sorted_sqrt_sum(best, k) / (double)k;
 }
 
 // cloud mean, Bessel-corrected standard deviation and the threshold.  Two passes (sum, then squared
