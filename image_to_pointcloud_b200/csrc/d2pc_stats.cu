@@ -120,7 +120,12 @@ __global__ void __launch_bounds__(kSelThreads, 1) sample_kernel(KParams kp) {
     uint32_t start = (uint32_t)(((unsigned long long)j * n) / S);
     uint32_t end = (uint32_t)(((unsigned long long)(j + 1) * n) / S);
     uint32_t idx = start + hash_u32(j * 0x9E3779B9u + (uint32_t)b * 0x85EBCA6Bu + 12345u) % (end - start);
-    float v = depth_at<NATIVE>(frame, kp, idx);
+    float v;
+    if (NATIVE) {  // one scattered 4-byte sample per load: ask L2 for a 64-byte fill instead of the default 128 (LDG.LTC64B)
+      asm volatile("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(frame + idx));
+    } else {
+      v = depth_at<NATIVE>(frame, kp, idx);
+    }
     k[e] = 0xFFFFFFFFu;
     if (is_finite_f32(v)) k[e] = float_to_key(v); else bad = true;
   }
