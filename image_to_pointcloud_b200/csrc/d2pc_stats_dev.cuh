@@ -500,12 +500,12 @@ __device__ __forceinline__ int select_phase_a(const KParams &kp, int b, int br, 
       } else if (v == Uf) c_eqU++;
     };
     uint32_t i = tid;
-    for (; i + 3u * nthr < m; i += 4u * nthr) {
-      float v[4];
+    for (; i + 7u * nthr < m; i += 8u * nthr) {  // eight independent L2 loads in flight per thread
+      float v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldcg(q + s_lo + i + (uint32_t)u * nthr);
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(q + s_lo + i + (uint32_t)u * nthr);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         if (cached) s_slice[i + (uint32_t)u * nthr] = v[u];
         visit(v[u]);
       }
@@ -612,8 +612,7 @@ __device__ __forceinline__ void select_phase_c(const KParams &kp, int b, int br,
     const bool shared_bin = vsh->shared_bin[br] != 0u;
     const bool own[2] = {vsh->want[br][0] != 0u, vsh->want[br][1] != 0u && !shared_bin};
     const uint32_t bin0 = vsh->bin[br][0], bin1 = vsh->bin[br][1];
-    for (uint32_t i = tid; i < m; i += nthr) {
-      const float v = cached ? s_slice[i] : __ldcg(q + s_lo + i);
+    auto collect = [&](float v) {
       if (v > Lf && v < Uf) {
         const uint32_t key = float_to_key(v);
         const uint32_t bk = (key - lo0) >> shift;
@@ -626,7 +625,18 @@ __device__ __forceinline__ void select_phase_c(const KParams &kp, int b, int br,
             atomicMax(&sh->mmax[br][t], key);
           }
       }
+    };
+    uint32_t i = tid;
+    if (!cached) {  // the slice comes from L2 again: eight independent loads in flight per thread
+      for (; i + 7u * nthr < m; i += 8u * nthr) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(q + s_lo + i + (uint32_t)u * nthr);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) collect(v[u]);
+      }
     }
+    for (; i < m; i += nthr) collect(cached ? s_slice[i] : __ldcg(q + s_lo + i));
   }
   __syncthreads();
   if (tid == 0) {
