@@ -177,6 +177,7 @@ constexpr size_t kEmitStageBytes = 2 * ((size_t)kEmitTile * 3 + 4) * sizeof(floa
 struct EmitSmall {  // static shared scratch of one emit tile
   uint32_t warp[kEmitThreads / 32];
   uint32_t b[6][kEmitThreads / 32];
+  uint32_t dest;   // MASK: the tile's first output row
 };
 
 // norm_fn(): called by every thread of the CTA after the tile's loads have been issued; returns a pointer to the
@@ -248,6 +249,10 @@ __device__ __forceinline__ bool emit_fast_tile(const KParams &kp, const EmitArgs
                byte_to_float(c2, D2PC_B1));
     }
   }
+  // MASK: the tile's first output row (written by mask_offsets_kernel before this launch) is fetched by one thread
+  // while the pixel loads are in flight and parked in shared memory: fetched where it is used (after the CTA scan)
+  // every thread waited a full L2 round trip for it, and fetched early by every thread it cost two live registers
+  if (MASK && tid == 0) es.dest = (uint32_t)(__ldg(kp.tile_state + (size_t)b * kp.emit_tiles + tile) >> 32);
   const NormParams *np_src = norm_fn();
   if (np_src == nullptr) return false;  // uniform
   if (p0 < P) {
@@ -325,7 +330,7 @@ __device__ __forceinline__ bool emit_fast_tile(const KParams &kp, const EmitArgs
     uint32_t local = warp_off + incl - my_cnt;
     // destination row: exclusive prefix of the kept counts, computed before this launch by
     // mask_count_kernel + mask_offsets_kernel (no inter-CTA dependency inside emit)
-    const uint32_t dest_row = (uint32_t)(kp.tile_state[(size_t)b * kp.emit_tiles + tile] >> 32);
+    const uint32_t dest_row = es.dest;   // (the barrier of the scan above ordered thread 0's store)
     const size_t g0 = ((size_t)(b + ea.frame0) * kp.g.N + dest_row) * 3;
     const uint32_t s_off = (uint32_t)(g0 & 3);
     const float col[12] = {
