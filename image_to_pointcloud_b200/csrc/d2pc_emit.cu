@@ -4,14 +4,15 @@
 //   BGR->RGB gather -> (depth-range mask -> ordered compaction) -> AoS float32 packing.
 //
 // Memory plan (HBM-bound by design: 4 B depth + 3 B BGR in, 24 B out per point):
-//   * emit_fast_kernel: stride 1, native-size depth, BGR, no mask.  Each thread owns 4
-//     consecutive pixels: one 16 B depth load, three 4 B colour loads, FP64 chain in registers,
-//     12-byte AoS records staged through shared memory so that every global store is a full,
-//     16 B-aligned, coalesced st.global.cs.v4 (streaming: the output is never re-read).
-//   * emit_generic_kernel: any stride / resized depth / BGRA / grey / mask.  Same staging; the
-//     compacted rows of a tile go to `prefix` rows found by a decoupled look-back over the
-//     frame's tiles, so the output keeps raster order (the reference's preview stride
-//     points[::stride], app.py:498-500, depends on it).
+//   * emit_fast_kernel<STEP, MASK, BOUNDS>: 3-channel image, any density (STEP 1 / 2 / 4), with or without the
+//     depth-range mask.  Each thread owns 4 consecutive output rows of one image row: vector loads of the sampled
+//     sectors, FP64 chain in registers, 12-byte AoS records staged through shared memory and handed to the TMA unit
+//     as one bulk copy per array and CTA (cp.async.bulk.global.shared::cta).  MASK: the tile's first output row
+//     comes from mask_count_kernel + mask_offsets_kernel, the rows are compacted inside the tile.
+//   * emit_generic_kernel: BGRA / grey images, widths that do not fit the vector tiling, smooth=True.  Same
+//     staging; the compacted rows of a tile go to `prefix` rows found by a decoupled look-back over the frame's
+//     tiles.  Either way the output keeps raster order (the reference's preview stride points[::stride],
+//     app.py:498-500, depends on it).
 #include <stdlib.h>
 
 #include "d2pc_emit_dev.cuh"

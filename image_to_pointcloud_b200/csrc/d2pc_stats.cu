@@ -2,19 +2,24 @@
 // exact 2nd/98th-percentile order statistics of every frame's (virtually resized) depth map,
 // non-finite repair (np.nanmedian) and the frame's normalisation parameters.
 //
-// Fast path (3 launches per batch, depth map read from HBM exactly once):
+// Fast path (3-4 launches per batch, depth map read from HBM exactly once):
 //   sample_kernel  1 CTA/frame   stratified sample (registers) -> exact sample order statistics
-//                                by a multi-level bucket histogram -> key brackets [L, U]
+//                                (bucket histogram + member pick) -> key brackets [L, U]
 //                                that contain the wanted ranks with ~6 sigma margin
-//   scan_kernel    streaming     per pixel, branch-free: count values below each bracket and
-//                                defer the few values inside a bracket (about 2% each) or
-//                                non-finite to the frame's raw queue.  Pure compares, no
-//                                histogram; the only atomics are per CTA.
-//   select_kernel  2 CTA/frame   classify the queued values against the bracket (equal to a
-//                                bound / strictly inside), resolve the wanted ranks, exact
-//                                selection inside the bracket (multi-level bucket histogram over
-//                                the L2-resident queue); the last CTA of a frame evaluates
-//                                NumPy's _lerp in float64 and writes the parameter block.
+//   scan_*_kernel  streaming     per pixel, 4 instructions: values strictly between the two brackets
+//                                (about 94%) need nothing; everything else, and every NaN, is deferred
+//                                to the frame's two raw queues (one reservation per CTA).  Native
+//                                depth, large grids: several tiles per CTA with the next tile's loads
+//                                in flight during a tile's epilogue (scan_native_multi_kernel);
+//                                resized depth: the interpolation is fused (scan_resized_tiled_kernel)
+//   select_kernel  2 CTA/frame   classify the queued values against the bracket (below / equal to a
+//                                bound / strictly inside), resolve the wanted ranks, exact selection
+//                                inside the bracket (bucket histogram over the L2-resident queue, then
+//                                the members of the wanted buckets); the last CTA of a frame evaluates
+//                                NumPy's _lerp in float64 and writes the parameter block.  Small
+//                                batches and 4K frames: K CTAs per bracket in two launches
+//                                (select_a_kernel, select_c_kernel); one or two frames: scan and
+//                                selection in one index-ordered launch (stats_ordered_kernel)
 // Frames the fast path cannot finish *exactly* (non-finite values, bracket miss, queue
 // overflow, collapsed percentiles) are only marked; d2pc_stats_fallback_enqueue runs the
 // input-agnostic exact path (8-bit radix select, nanmedian repair) for those.
