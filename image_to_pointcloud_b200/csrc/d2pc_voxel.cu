@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(256) vox_clear_kernel(VoxTable t, const uint32
 // L2 residency: the 4-byte slot table (66 MB for a 4K frame) is what is probed at random and must stay in the
 // 126 MB L2; the keys and accumulators (8 + 40 bytes per row) stream through and would push it out (ncu: 70% of the
 // claim kernel's CAS sectors missed L2).  Slots are cleared evict-last, streamed arrays are touched evict-first.
+__device__ __forceinline__ float ldg_f32_pol(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void red_add_u64_pol(unsigned long long *p, unsigned long long v, uint64_t pol) {
   asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(pol) : "memory");
 }
@@ -277,8 +282,9 @@ __global__ void __launch_bounds__(kVoxThreads, 4) vox_insert_kernel(VoxTable t, 
     run.cnt_r = run.g_b = run.sx = run.sy = run.sz = 0ull;
     if (i < M) {
       const float *p = xyz + 3 * (size_t)i, *c = rgb + 3 * (size_t)i;
-      const float x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2);
-      const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+      // the rows stream through once: evict-first, like every other streamed array of the stage
+      const float x0 = ldg_f32_pol(p, pol_stream), x1 = ldg_f32_pol(p + 1, pol_stream), x2 = ldg_f32_pol(p + 2, pol_stream);
+      const float c0 = ldg_f32_pol(c, pol_stream), c1 = ldg_f32_pol(c + 1, pol_stream), c2 = ldg_f32_pol(c + 2, pol_stream);
       const double o0 = (double)x0 - vmin0, o1 = (double)x1 - vmin1, o2 = (double)x2 - vmin2;
       // floor((p - vmin) / vs): correctly rounded quotient from the reciprocal (d2pc_math.h).  The unguarded form is
       // enough here: offsets are >= 0; a quotient so small that the residual steps underflow floors to 0 either way,
