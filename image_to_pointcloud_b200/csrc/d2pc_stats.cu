@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kScanThreads, MINB) scan_native_multi_kernel(K
   const uint32_t t0 = blockIdx.x * (uint32_t)TPC;
   const float U0 = bracket_hi_float(fs->brU[0]), L1 = bracket_lo_float(fs->brL[1]);
   const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sm.pq[0][tid]);
-  const uint64_t pol = l2_policy(false, (kp.hints & kHintScanKeep) != 0);
+  const uint64_t pol = l2_policy((kp.hints & kHintScanKeep) == 0, (kp.hints & kHintScanKeep) != 0);   // one stage: the map streams through (evict-first)
   auto full = [&](uint32_t tile) { return vec_ok && tile < ntiles && (tile + 1u) * (uint32_t)kPx <= n; };
   float4 r[PT / 4];
   if (full(t0)) {

@@ -94,12 +94,15 @@ __device__ __forceinline__ void scan_flush(const float *pq, uint32_t nq, float U
   const uint32_t excl = woff + incl - packed;
   // offsets into the frame's queue pair (queue 1 starts cand_cap floats after queue 0)
   uint32_t o0 = sm.gbase[0] + (excl & 0xFFFFu), o1 = sm.gbase[1] + (excl >> 16);
+  // the queues are what the selection reads next: evict-last, so that the depth map streaming through L2 (1 GB per
+  // 128 frames) does not push them out to DRAM before the selection runs
+  const uint64_t pol_keep = l2_policy(false, true);
   if (o0 + (packed & 0xFFFFu) <= kp.cand_cap && o1 + (packed >> 16) <= kp.cand_cap) {
     o1 += kp.cand_cap;
     for (uint32_t j = 0; j < nq; ++j) {
       const float v = pq[j * kScanThreads + tid];
-      if (!(v > U0)) gq0[o0++] = v;
-      if (v >= L1) gq0[o1++] = v;
+      if (!(v > U0)) stg_f1_pol(gq0 + o0++, v, pol_keep);
+      if (v >= L1) stg_f1_pol(gq0 + o1++, v, pol_keep);
     }
   } else {  // a queue overflows (the frame will take the fallback): drop what does not fit
     for (uint32_t j = 0; j < nq; ++j) {
@@ -133,7 +136,7 @@ __device__ __forceinline__ void scan_tile(const KParams &kp, int b, uint32_t til
   const uint32_t tile_base = tile * (uint32_t)kTilePx;
   if (vec_ok && tile_base + (uint32_t)kTilePx <= n) {
     const float *src = frame + tile_base + 4u * (uint32_t)tid;
-    const uint64_t pol = l2_policy(false, (kp.hints & kHintScanKeep) != 0);
+    const uint64_t pol = l2_policy((kp.hints & kHintScanKeep) == 0, (kp.hints & kHintScanKeep) != 0);   // one stage: the map streams through (evict-first)
     float4 r[kTilePerThread / 4];
 #pragma unroll
     for (int j = 0; j < kTilePerThread / 4; ++j) r[j] = ldg_f4_pol(src + (size_t)j * (4 * kScanThreads), pol);
