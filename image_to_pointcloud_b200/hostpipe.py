@@ -20,6 +20,19 @@ from .engine import FrameEngine
 N_SLOTS = 3
 
 
+def plan_chunks(n: int, chunk: int) -> List[Tuple[int, int]]:
+    """(start, count) of every chunk of an n-frame run: a short first chunk (the copy-out stream starts after a
+    quarter of a chunk's upload instead of a whole one), then full chunks, then the remainder.  Every frame is in
+    exactly one chunk, no chunk is longer than ``chunk``."""
+    out, s = [], 0
+    first = min(n, max(1, chunk // 4)) if n > chunk else min(n, chunk)
+    while s < n:
+        c = first if s == 0 else min(chunk, n - s)
+        out.append((s, c))
+        s += c
+    return out
+
+
 class HostFramePipeline:
     def __init__(self, img_h: int, img_w: int, dep_h: Optional[int] = None, dep_w: Optional[int] = None, *,
                  img_c: int = 3, chunk: int = 8, density: str = "high", invert: bool = True,
@@ -67,16 +80,7 @@ class HostFramePipeline:
 
     # -- the pipeline ---------------------------------------------------------------------
     def chunks(self, n: int) -> List[Tuple[int, int]]:
-        """(start, count) of every chunk: a short first chunk (the copy-out stream starts after a quarter of a
-        chunk's upload instead of a whole one), then full chunks, then the remainder."""
-        B = self.chunk
-        out, s = [], 0
-        first = min(n, max(1, B // 4)) if n > B else min(n, B)
-        while s < n:
-            c = first if s == 0 else min(B, n - s)
-            out.append((s, c))
-            s += c
-        return out
+        return plan_chunks(n, self.chunk)
 
     def run_pinned(self, images: Optional[torch.Tensor], depths: torch.Tensor, out_xyz: torch.Tensor,
                    out_rgb: torch.Tensor, out_counts: torch.Tensor) -> None:

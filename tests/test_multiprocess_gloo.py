@@ -120,3 +120,20 @@ def test_multi_gpu_pipeline_orchestration_on_cpu():
     bad = MultiGpuPipeline(2, 2, devices=[0, "boom", 2], pipeline_factory=Fake)
     with pytest.raises(ValueError):
         bad.run_pinned(None, depths, xyz, rgb, counts)
+
+
+def test_host_pipeline_chunk_plan():
+    """HostFramePipeline's chunking: every frame in exactly one chunk, in order, none longer than the engine's
+    batch, the first one short when there is more than one chunk."""
+    sys.path.insert(0, ROOT)
+    from image_to_pointcloud_b200.hostpipe import plan_chunks
+    for chunk in (1, 2, 3, 4, 8, 16):
+        for n in (0, 1, 2, 3, 7, 8, 9, 31, 32, 33, 100):
+            plan = plan_chunks(n, chunk)
+            flat = [i for s0, c in plan for i in range(s0, s0 + c)]
+            assert flat == list(range(n)), (chunk, n)
+            assert all(0 < c <= chunk for _, c in plan), (chunk, n)
+            if n > chunk:
+                assert plan[0][1] == max(1, chunk // 4)
+            elif n:
+                assert plan == [(0, n)]
