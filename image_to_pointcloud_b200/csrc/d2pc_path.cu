@@ -298,7 +298,9 @@ int path_body(D2pcPath *p, const PathArgs &a, cudaStream_t s_main) {
   const int n_emit = overlap ? env_int("D2PC_PATH_EMIT", 2, 1, kMaxEmit) : 1;
   const bool sample_first = n_sub > 1 && env_int("D2PC_PATH_SAMPLE_FIRST", 1, 0, 1) != 0;
   const bool ring = kp.resized != nullptr && n_sub > 1;
-  kp.hints = (a.flags & D2PC_PATH_NO_L2_HINTS) ? 0 : (n_sub > 1 ? kHintPipeline : 0);
+  // one stage: nothing is read twice from L2, so everything the emit touches is marked evict-first (its depth
+  // and colour loads are last uses, its rows are never re-read): measured 1.527 against 1.538 ms per 128 frames
+  kp.hints = (a.flags & D2PC_PATH_NO_L2_HINTS) ? 0 : (n_sub > 1 ? kHintPipeline : (kHintEmitDepthFirst | kHintStreamFirst));
   // a ring slot is rewritten while its lines are still dirty in L2: do not demote them after the emit's read
   if (ring) kp.hints &= ~kHintEmitDepthFirst;
   if (const char *h = getenv("D2PC_HINTS")) kp.hints = atoi(h);  // measurement aid
